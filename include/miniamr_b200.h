@@ -1,0 +1,177 @@
+/* miniamr_b200 — C ABI of the B200-native miniAMR stage hot path.
+ *
+ * The reference (Mantevo/miniAMR, ref/) has no plugin or FFI layer: its hot
+ * path is a set of plain C functions that share state through globals
+ * (SURVEY.md §8b).  This header is the boundary a maintainer binds instead:
+ * plain pointers and sizes, no CUDA or torch types.  Each entry point cites the
+ * reference routine (file:line under ref/) it replaces.  integration/glue.c
+ * shows the reference-side binding: it exports the reference's own symbols
+ * comm / stencil_driver / check_sum / pack_block / unpack_block on top of this
+ * ABI by marshalling the reference's globals.
+ *
+ * All block data lives in a device-resident pool:
+ *     pool[var][slot][tile],  tile = (nx+2)(ny+2)(nz+2) doubles, k fastest,
+ *     ghosts at index 0 and n+1 exactly like block.array[var][i][j][k]
+ *     (block.h:52; allocation main.c:429-450), tile stride padded to 128 B.
+ * `slot` is the reference's index into blocks[] (0 <= slot < max_blocks).
+ *
+ * There is NO CPU fallback: every call fails (non-zero return, message via
+ * mamr_last_error) if CUDA is unavailable.
+ *
+ * Threading: like the reference, one host thread per context; calls are
+ * executed in call order.  Everything except mamr_check_sum*, mamr_download_*,
+ * mamr_pack_block and mamr_sync is asynchronous with respect to the host.
+ */
+#ifndef MINIAMR_B200_H
+#define MINIAMR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAMR_ABI_VERSION 1
+
+typedef struct mamr_ctx mamr_ctx;
+
+/* The command-line parameters the path depends on (main.c:57-174, param.h). */
+typedef struct {
+   int nx, ny, nz;      /* --nx --ny --nz: cells per block edge (even, > 0)      */
+   int num_vars;        /* --num_vars                                            */
+   int comm_vars;       /* --comm_vars; 0 or > num_vars means num_vars
+                           (main.c:711-712)                                      */
+   int max_blocks;      /* --max_blocks: pool slots on this rank                 */
+   int stencil;         /* --stencil: 7 or 27 (0, the variable-work mix, is not
+                           on this path yet -> MAMR_EUNSUPPORTED)                */
+   int code;            /* --code: 0 (1 and 2 -> MAMR_EUNSUPPORTED)              */
+   int permute;         /* --permute (comm.c:45-55)                              */
+   int device;          /* CUDA device ordinal, -1 = current device              */
+   int rank, num_ranks; /* my_pe, num_pes: one process per GPU                   */
+} mamr_params;
+
+/* What the path reads of one active block (block.h:36-53). */
+typedef struct {
+   int slot;            /* sorted_list[in].n                                     */
+   int level;           /* blocks[slot].level                                    */
+   int nei_level[6];    /* W,E,S,N,D,U; -2 = domain boundary                     */
+   int nei[6][2][2];    /* neighbour slot(s); negative = off rank (-1 - rank)    */
+} mamr_block;
+
+/* One direction of the reference's off-rank comm lists (comm.h:38-55,
+ * built by comm_util.c:36-229).  Offsets and sizes are in doubles. */
+typedef struct {
+   int num_partners;        /* num_comm_partners[dir]                            */
+   const int *partner;      /* comm_partner[dir][i]: rank                        */
+   const int *index;        /* comm_index[dir][i]: first face of partner i       */
+   const int *num;          /* comm_num[dir][i]: faces of partner i              */
+   const int *send_size;    /* send_size[dir][i]                                 */
+   const int *recv_size;    /* recv_size[dir][i]                                 */
+   int num_cases;           /* num_cases[dir]: total faces                       */
+   const int *block;        /* comm_block[dir][f]: local slot                    */
+   const int *face_case;    /* comm_face_case[dir][f]                            */
+   const int *send_off;     /* comm_send_off[dir][f]                             */
+   const int *recv_off;     /* comm_recv_off[dir][f]                             */
+} mamr_comm_dir;
+
+/* Counters the reference's profile.c consumes (timer.h:118-131,
+ * block.h:144-146); the binding adds them to the reference globals. */
+typedef struct {
+   long long counter_same[3], counter_diff[3], counter_bc[3];   /* comm.c:169,178,189,196 */
+   long long counter_halo_send[3], counter_halo_recv[3];        /* comm.c:81,152          */
+   long long counter_face_send[3], counter_face_recv[3];        /* comm.c:143,226         */
+   double size_mesg_send[3], size_mesg_recv[3];                 /* bytes, comm.c:82,153;
+                                                                   = NVLink bytes of ghost traffic */
+   double total_fp_adds, total_fp_divs;                         /* stencil.c:100-101,142-143 */
+   long long total_red;                                         /* check_sum.c:62         */
+   long long kernel_launches;                                   /* CUDA kernels launched  */
+   double migrate_bytes;                                        /* block payload bytes moved */
+} mamr_counters;
+
+enum { MAMR_OK = 0, MAMR_ECUDA = 1, MAMR_EINVAL = 2, MAMR_EUNSUPPORTED = 3,
+       MAMR_ETOPOLOGY = 4, MAMR_ENCCL = 5 };
+
+/* ---- lifecycle: replaces the block-array part of allocate()/deallocate(),
+ *      main.c:429-450, 613-624 ------------------------------------------- */
+int  mamr_abi_version(void);
+int  mamr_create(const mamr_params *params, mamr_ctx **out);
+void mamr_destroy(mamr_ctx *ctx);
+const char *mamr_last_error(void);
+int  mamr_sync(mamr_ctx *ctx);                       /* drain all queued work   */
+int  mamr_get_counters(mamr_ctx *ctx, mamr_counters *out);
+int  mamr_reset_counters(mamr_ctx *ctx);
+long long mamr_tile_doubles(mamr_ctx *ctx);          /* (nx+2)(ny+2)(nz+2)      */
+long long mamr_pool_bytes(mamr_ctx *ctx);
+/* device pointer of the pool (for zero-copy users, e.g. torch tensors in
+ * bench.py) and its strides in doubles */
+void *mamr_pool_device_ptr(mamr_ctx *ctx, long long *var_stride, long long *slot_stride);
+
+/* ---- block data in / out: replaces the fill loops init.c:484-495 --------
+ * host layout: tiles[var][i][j][k] with ghosts, (nx+2)(ny+2)(nz+2) doubles
+ * per var, num_vars tiles per block.                                        */
+int mamr_upload_block(mamr_ctx *ctx, int slot, const double *tiles);
+int mamr_download_block(mamr_ctx *ctx, int slot, double *tiles);
+int mamr_upload_tile(mamr_ctx *ctx, int slot, int var, const double *tile);
+int mamr_download_tile(mamr_ctx *ctx, int slot, int var, double *tile);
+int mamr_zero_block(mamr_ctx *ctx, int slot);
+
+/* ---- topology: what comm()/stencil_calc()/check_sum() read through the
+ *      globals blocks[], sorted_list, sorted_index (block.h:36-77) and the
+ *      comm lists (comm.h:38-55).  Call after init()/refine()/load balance,
+ *      i.e. whenever the host mutated them. -------------------------------- */
+int mamr_set_topology(mamr_ctx *ctx, int num_active, const mamr_block *sorted_blocks);
+int mamr_set_comm_lists(mamr_ctx *ctx, const mamr_comm_dir dirs[3]);
+
+/* ---- the stage hot path ------------------------------------------------- */
+/* comm(start, num_comm, stage): comm.c:42-242 (code 0: pack_face :254-401,
+ * unpack_face :1002-1150, on_proc_comm :1473-1534, on_proc_comm_diff
+ * :1597-1688, apply_bc :1911-1965) */
+int mamr_comm(mamr_ctx *ctx, int start, int num_comm, int stage);
+/* stencil_driver(var, calc_stage): stencil.c:43-74 -> stencil_calc :76-145 */
+int mamr_stencil_driver(mamr_ctx *ctx, int var, int calc_stage);
+/* north_star alias: stencil_calc(var) == stencil_driver(var, 0) for 7/27 */
+int mamr_stencil_calc(mamr_ctx *ctx, int var);
+/* the same for a run of variables in one launch */
+int mamr_stencil_vars(mamr_ctx *ctx, int var_start, int num);
+/* check_sum(var): check_sum.c:36-65, including the global reduction
+ * (ncclAllReduce when num_ranks > 1).  Returns the sum in *sum. */
+int mamr_check_sum(mamr_ctx *ctx, int var, double *sum);
+int mamr_check_sum_vars(mamr_ctx *ctx, int var_start, int num, double *sums);
+/* one whole stage as driver.c:73-89 issues it (comm per group of comm_vars,
+ * stencil per variable), without the host round trips */
+int mamr_stage(mamr_ctx *ctx, int stage);
+
+/* ---- refinement / migration data movement ------------------------------- */
+/* split_blocks() data copy, block.c:143-173: octant o of parent -> child o */
+int mamr_split_block(mamr_ctx *ctx, int parent_slot, const int child_slots[8]);
+/* consolidate_blocks() data copy, block.c:411-431 */
+int mamr_consolidate_block(mamr_ctx *ctx, const int child_slots[8], int parent_slot);
+/* pack_block()/unpack_block() payload, pack.c:66-70 / 103-107: interiors
+ * only, var-major then i,j,k: num_vars*nx*ny*nz doubles (host memory) */
+int mamr_pack_block(mamr_ctx *ctx, int slot, double *payload);
+int mamr_unpack_block(mamr_ctx *ctx, int slot, const double *payload);
+/* the same payload GPU-to-GPU over NCCL (replaces MPI_Send/Irecv of
+ * rcb.c:237,261): both ranks call, one as sender one as receiver */
+int mamr_send_block(mamr_ctx *ctx, int slot, int dest_rank);
+int mamr_recv_block(mamr_ctx *ctx, int slot, int src_rank);
+
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink ------------------- */
+#define MAMR_NCCL_ID_BYTES 128
+int mamr_nccl_get_unique_id(char id[MAMR_NCCL_ID_BYTES]);   /* rank 0, then broadcast
+                                                               over the host channel */
+int mamr_nccl_init(mamr_ctx *ctx, const char id[MAMR_NCCL_ID_BYTES]);
+
+/* ---- measurement helpers (bench.py) ------------------------------------- */
+/* CUDA-event timing on the library's own stream: mark begin/end around any
+ * sequence of calls; elapsed in milliseconds. */
+int mamr_timer_begin(mamr_ctx *ctx);
+int mamr_timer_end(mamr_ctx *ctx, float *ms);
+/* accumulated device time of the stencil kernel launches since the last
+ * reset (events recorded around every stencil launch when enabled) */
+int mamr_kernel_timing(mamr_ctx *ctx, int enable);
+int mamr_kernel_time_ms(mamr_ctx *ctx, float *stencil_ms, float *ghost_ms,
+                        float *checksum_ms, long long *stencil_launches,
+                        long long *ghost_launches, long long *checksum_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

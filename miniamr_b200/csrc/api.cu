@@ -1,0 +1,1120 @@
+// C ABI of the B200-native miniAMR stage hot path (include/miniamr_b200.h).
+// Host-side orchestration only: device pool, topology -> ghost descriptors,
+// direction phases, NCCL send/recv of ghost faces and migrated blocks, deferred
+// per-variable stencil launches.  All arithmetic is in the kernels
+// (stencil.cu, ghost.cu, reduce_refine.cu).  There is no CPU fallback.
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace mamr;
+
+// ---------------------------------------------------------------------------
+// NCCL, resolved at run time so that single-GPU users never need it.
+// ---------------------------------------------------------------------------
+namespace {
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { NCCL_DOUBLE = 8, NCCL_SUM = 0 };
+struct NcclApi {
+   void *handle = nullptr;
+   int (*GetUniqueId)(ncclUniqueId *) = nullptr;
+   int (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+   int (*CommDestroy)(ncclComm_t) = nullptr;
+   int (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+   int (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+   int (*AllReduce)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+   int (*GroupStart)() = nullptr;
+   int (*GroupEnd)() = nullptr;
+   const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...)
+{
+   char buf[1024];
+   va_list ap;
+   va_start(ap, fmt);
+   vsnprintf(buf, sizeof buf, fmt, ap);
+   va_end(ap);
+   g_err = buf;
+   return code;
+}
+
+bool load_nccl()
+{
+   if (g_nccl.handle) return true;
+   const char *names[] = { getenv("MAMR_NCCL_LIB"), "libnccl.so.2", "libnccl.so" };
+   void *h = nullptr;
+   for (const char *n : names)
+      if (n && (h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+   if (!h) return false;
+#define SYM(field, name)                                              \
+   *(void **)(&g_nccl.field) = dlsym(h, name);                        \
+   if (!g_nccl.field) return false;
+   SYM(GetUniqueId, "ncclGetUniqueId")
+   SYM(CommInitRank, "ncclCommInitRank")
+   SYM(CommDestroy, "ncclCommDestroy")
+   SYM(Send, "ncclSend")
+   SYM(Recv, "ncclRecv")
+   SYM(AllReduce, "ncclAllReduce")
+   SYM(GroupStart, "ncclGroupStart")
+   SYM(GroupEnd, "ncclGroupEnd")
+   SYM(GetErrorString, "ncclGetErrorString")
+#undef SYM
+   g_nccl.handle = h;
+   return true;
+}
+}  // namespace
+
+#define CU(call)                                                                          \
+   do {                                                                                   \
+      cudaError_t e_ = (call);                                                            \
+      if (e_ != cudaSuccess)                                                              \
+         return fail(MAMR_ECUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_),      \
+                     __FILE__, __LINE__, cudaGetErrorString(e_));                         \
+   } while (0)
+#define NC(call)                                                                          \
+   do {                                                                                   \
+      int r_ = (call);                                                                    \
+      if (r_ != 0)                                                                        \
+         return fail(MAMR_ENCCL, "NCCL error at %s:%d: %s", __FILE__, __LINE__,           \
+                     g_nccl.GetErrorString ? g_nccl.GetErrorString(r_) : "?");            \
+   } while (0)
+#define CK(call)                     \
+   do {                              \
+      int r_ = (call);               \
+      if (r_ != MAMR_OK) return r_;  \
+   } while (0)
+
+struct DirLists {
+   std::vector<int> partner, index, num, send_size, recv_size;
+   std::vector<int> block, face_case, send_off, recv_off;
+};
+
+struct EventPair { cudaEvent_t a, b; int cls; };
+
+struct mamr_ctx {
+   mamr_params p;
+   Geometry g;
+   int comm_vars;
+   double *pool = nullptr;
+   size_t pool_bytes = 0;
+   cudaStream_t stream = nullptr;
+
+   int num_active = 0;
+   std::vector<mamr_block> blocks;
+   int *d_slots = nullptr;
+   size_t slots_cap = 0;
+
+   // ghost descriptors, per direction: [local | pack] contiguous, then unpack
+   std::vector<FaceOp> ops_main[3], ops_unpack[3];
+   FaceOp *d_ops = nullptr;
+   size_t ops_cap = 0;
+   size_t off_main[3] = {0, 0, 0}, off_unpack[3] = {0, 0, 0};
+   bool ops_dirty = true;
+   long long n_same[3], n_diff[3], n_bc[3];
+
+   DirLists cl[3];
+   bool have_partners = false;
+   double *d_send[3] = {nullptr, nullptr, nullptr}, *d_recv[3] = {nullptr, nullptr, nullptr};
+   size_t send_cap[3] = {0, 0, 0}, recv_cap[3] = {0, 0, 0};
+
+   double *d_partials = nullptr;
+   size_t partials_cap = 0;
+   double *d_sums = nullptr, *h_sums = nullptr;
+   std::vector<char> cs_valid;
+   std::vector<double> cs_cache;
+   bool modified_since_cs = true;
+
+   int pend_start = 0, pend_num = 0;
+
+   RefineOp *d_rops = nullptr;
+   int rops_cap = 4096, rops_pos = 0;
+   double *d_payload = nullptr;
+   double *h_stage = nullptr;   // pinned, one block
+
+   mamr_counters cnt;
+
+   ncclComm_t nccl = nullptr;
+
+   cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+   bool ktiming = false;
+   std::vector<EventPair> kev;
+   std::vector<cudaEvent_t> ev_free;
+   double k_ms[3] = {0, 0, 0};
+   long long k_launches[3] = {0, 0, 0};
+};
+
+namespace {
+
+enum { KC_STENCIL = 0, KC_GHOST = 1, KC_CHECKSUM = 2 };
+
+struct KTimer {
+   mamr_ctx *c;
+   EventPair ep;
+   bool on;
+   KTimer(mamr_ctx *c_, int cls) : c(c_), on(c_->ktiming)
+   {
+      if (!on) return;
+      for (cudaEvent_t *e : { &ep.a, &ep.b }) {
+         if (!c->ev_free.empty()) {
+            *e = c->ev_free.back();
+            c->ev_free.pop_back();
+         } else
+            cudaEventCreate(e);
+      }
+      ep.cls = cls;
+      cudaEventRecord(ep.a, c->stream);
+   }
+   ~KTimer()
+   {
+      if (!on) return;
+      cudaEventRecord(ep.b, c->stream);
+      c->kev.push_back(ep);
+   }
+};
+
+void drain_ktimers(mamr_ctx *c)
+{
+   for (EventPair &ep : c->kev) {
+      float ms = 0.f;
+      cudaEventSynchronize(ep.b);
+      cudaEventElapsedTime(&ms, ep.a, ep.b);
+      c->k_ms[ep.cls] += ms;
+      c->k_launches[ep.cls]++;
+      c->ev_free.push_back(ep.a);
+      c->ev_free.push_back(ep.b);
+   }
+   c->kev.clear();
+}
+
+// in-face axes in buffer order (slow, fast): comm.c:266-270, 311-320, 361-370
+inline void face_axes(int d, int &sa, int &fa)
+{
+   sa = (d == 0) ? 1 : 0;
+   fa = (d == 2) ? 1 : 2;
+}
+
+// whole-face extent of in-face axis ax: widened to 0..n+1 for the axes of the
+// directions exchanged earlier when edges/corners must travel
+// (comm.c:1496-1527, 306-320, 356-370)
+inline void whole_extent(const Geometry &g, bool wide, int d, int ax, int &lo, int &hi)
+{
+   if (wide && ax < d) { lo = 0; hi = g.n[ax] + 1; }
+   else { lo = 1; hi = g.n[ax]; }
+}
+
+inline long long tile_base(const Geometry &g, int slot) { return (long long)slot*g.tile_stride; }
+
+FaceOp tile_copy(const Geometry &g, int d, int dst_slot, int dst_plane, int src_slot,
+                 int src_plane, int s0, int s1, int f0, int f1)
+{
+   int sa, fa;
+   face_axes(d, sa, fa);
+   FaceOp op;
+   const long long inplane = (long long)s0*g.str[sa] + (long long)f0*g.str[fa];
+   op.dst_base = tile_base(g, dst_slot) + (long long)dst_plane*g.str[d] + inplane;
+   op.src_base = tile_base(g, src_slot) + (long long)src_plane*g.str[d] + inplane;
+   op.dst_vs = op.src_vs = g.var_stride;
+   op.dst_S = op.src_S = g.str[sa];
+   op.dst_F = op.src_F = g.str[fa];
+   op.Ns = s1 - s0 + 1;
+   op.Nf = f1 - f0 + 1;
+   op.mode = FM_COPY;
+   op.mem = 0;
+   return op;
+}
+
+// on_proc_comm, comm.c:1473-1534: lo = block on the minus side of the face
+void add_same(mamr_ctx *c, int d, int lo, int hi)
+{
+   const Geometry &g = c->g;
+   int sa, fa, s0, s1, f0, f1;
+   face_axes(d, sa, fa);
+   const bool wide = c->p.stencil != 7;
+   whole_extent(g, wide, d, sa, s0, s1);
+   whole_extent(g, wide, d, fa, f0, f1);
+   c->ops_main[d].push_back(tile_copy(g, d, lo, g.n[d] + 1, hi, 1, s0, s1, f0, f1));
+   c->ops_main[d].push_back(tile_copy(g, d, hi, 0, lo, g.n[d], s0, s1, f0, f1));
+}
+
+// on_proc_comm_diff, comm.c:1597-1688: cs coarse slot, fs fine slot, l = face of
+// the coarse block; jq picks the half along the slow axis, iq along the fast one
+void add_diff(mamr_ctx *c, int cs, int fs, int l, int iq, int jq)
+{
+   const Geometry &g = c->g;
+   const int d = l/2;
+   int sa, fa;
+   face_axes(d, sa, fa);
+   const int hs = g.n[sa]/2, hf = g.n[fa]/2, os = jq*hs, of = iq*hf;
+   int c_ghost, c_src, f_ghost, f_src;
+   if (l%2 == 0) { c_ghost = 0; c_src = 1; f_ghost = g.n[d] + 1; f_src = g.n[d]; }
+   else { c_ghost = g.n[d] + 1; c_src = g.n[d]; f_ghost = 0; f_src = 1; }
+   const long long S = g.str[sa], F = g.str[fa], N = g.str[d];
+   FaceOp pro;   // coarse -> fine ghosts: value/4 replicated 2x2
+   pro.dst_base = tile_base(g, fs) + f_ghost*N + S + F;
+   pro.src_base = tile_base(g, cs) + c_src*N + (1 + os)*S + (1 + of)*F;
+   pro.dst_vs = pro.src_vs = g.var_stride;
+   pro.dst_S = pro.src_S = (int)S;
+   pro.dst_F = pro.src_F = (int)F;
+   pro.Ns = g.n[sa];
+   pro.Nf = g.n[fa];
+   pro.mode = FM_PROLONG;
+   pro.mem = 0;
+   c->ops_main[d].push_back(pro);
+   FaceOp res;   // fine -> coarse ghost quarter: 4-term sum
+   res.dst_base = tile_base(g, cs) + c_ghost*N + (1 + os)*S + (1 + of)*F;
+   res.src_base = tile_base(g, fs) + f_src*N + S + F;
+   res.dst_vs = res.src_vs = g.var_stride;
+   res.dst_S = res.src_S = (int)S;
+   res.dst_F = res.src_F = (int)F;
+   res.Ns = hs;
+   res.Nf = hf;
+   res.mode = FM_SUM4;
+   res.mem = 0;
+   c->ops_main[d].push_back(res);
+}
+
+// apply_bc, comm.c:1911-1965
+void add_bc(mamr_ctx *c, int slot, int l)
+{
+   const Geometry &g = c->g;
+   const int d = l/2;
+   int sa, fa;
+   face_axes(d, sa, fa);
+   const int to = (l%2) ? g.n[d] + 1 : 0, from = (l%2) ? g.n[d] : 1;
+   int s0 = 1, s1 = g.n[sa], f0 = 1, f1 = g.n[fa];
+   if (c->p.stencil != 7) { s0 = 0; s1 = g.n[sa] + 1; f0 = 0; f1 = g.n[fa] + 1; }
+   c->ops_main[d].push_back(tile_copy(g, d, slot, to, slot, from, s0, s1, f0, f1));
+}
+
+// quarter of a coarse face, cases 6-9 (comm.c:282-295, 1029-1042)
+inline void quarter_range(const Geometry &g, int fc, int sa, int fa, int &s0, int &s1,
+                          int &f0, int &f1)
+{
+   const int hs = g.n[sa]/2, hf = g.n[fa]/2;
+   if (fc%2 == 0) { s0 = 1; s1 = hs; } else { s0 = hs + 1; s1 = g.n[sa]; }
+   if ((fc/2)%2 == 1) { f0 = 1; f1 = hf; } else { f0 = hf + 1; f1 = g.n[fa]; }
+}
+
+// pack_face code 0, comm.c:254-401 -> device send buffer at comm_send_off
+void add_pack(mamr_ctx *c, int d, int slot, int fc, int off)
+{
+   const Geometry &g = c->g;
+   int sa, fa, s0, s1, f0, f1;
+   face_axes(d, sa, fa);
+   int plane = 1;
+   if (fc >= 10) { plane = g.n[d]; fc -= 10; }
+   const long long S = g.str[sa], F = g.str[fa], N = g.str[d];
+   FaceOp op;
+   op.mem = MEM_DST_SEND;
+   op.src_vs = g.var_stride;
+   op.src_S = (int)S;
+   op.src_F = (int)F;
+   if (fc < 2) {
+      whole_extent(g, fc == 1, d, sa, s0, s1);
+      whole_extent(g, fc == 1, d, fa, f0, f1);
+      op.mode = FM_COPY;
+      op.Ns = s1 - s0 + 1; op.Nf = f1 - f0 + 1;
+      op.src_base = tile_base(g, slot) + plane*N + s0*S + f0*F;
+   } else if (fc <= 5) {
+      op.mode = FM_SUM4;
+      op.Ns = g.n[sa]/2; op.Nf = g.n[fa]/2;
+      op.src_base = tile_base(g, slot) + plane*N + S + F;
+   } else {
+      quarter_range(g, fc, sa, fa, s0, s1, f0, f1);
+      op.mode = FM_DIV4;
+      op.Ns = s1 - s0 + 1; op.Nf = f1 - f0 + 1;
+      op.src_base = tile_base(g, slot) + plane*N + s0*S + f0*F;
+   }
+   op.dst_base = off;
+   op.dst_S = op.Nf;
+   op.dst_F = 1;
+   op.dst_vs = (long long)op.Ns*op.Nf;
+   c->ops_main[d].push_back(op);
+}
+
+// unpack_face code 0, comm.c:1002-1150 (the case is the receiver's own)
+void add_unpack(mamr_ctx *c, int d, int slot, int fc, int off)
+{
+   const Geometry &g = c->g;
+   int sa, fa, s0, s1, f0, f1;
+   face_axes(d, sa, fa);
+   int plane = 0;
+   if (fc >= 10) { plane = g.n[d] + 1; fc -= 10; }
+   const long long S = g.str[sa], F = g.str[fa], N = g.str[d];
+   FaceOp op;
+   op.mem = MEM_SRC_RECV;
+   op.dst_vs = g.var_stride;
+   op.dst_S = (int)S;
+   op.dst_F = (int)F;
+   op.src_base = off;
+   op.src_F = 1;
+   if (fc < 2) {
+      whole_extent(g, fc == 1, d, sa, s0, s1);
+      whole_extent(g, fc == 1, d, fa, f0, f1);
+      op.mode = FM_COPY;
+      op.Ns = s1 - s0 + 1; op.Nf = f1 - f0 + 1;
+      op.dst_base = tile_base(g, slot) + plane*N + s0*S + f0*F;
+      op.src_S = op.Nf;
+      op.src_vs = (long long)op.Ns*op.Nf;
+   } else if (fc <= 5) {
+      const int hs = g.n[sa]/2, hf = g.n[fa]/2;
+      op.mode = FM_REPL;
+      op.Ns = g.n[sa]; op.Nf = g.n[fa];
+      op.dst_base = tile_base(g, slot) + plane*N + S + F;
+      op.src_S = hf;
+      op.src_vs = (long long)hs*hf;
+   } else {
+      quarter_range(g, fc, sa, fa, s0, s1, f0, f1);
+      op.mode = FM_COPY;
+      op.Ns = s1 - s0 + 1; op.Nf = f1 - f0 + 1;
+      op.dst_base = tile_base(g, slot) + plane*N + s0*S + f0*F;
+      op.src_S = op.Nf;
+      op.src_vs = (long long)op.Ns*op.Nf;
+   }
+   c->ops_unpack[d].push_back(op);
+}
+
+// The on-rank loop of comm(), comm.c:162-203, flattened into descriptors.
+int build_ops(mamr_ctx *c)
+{
+   const int nb = c->num_active;
+   std::vector<int> slot2idx(c->p.max_blocks, -1);
+   for (int a = 0; a < nb; a++) slot2idx[c->blocks[a].slot] = a;
+   for (int d = 0; d < 3; d++) {
+      c->ops_main[d].clear();
+      c->ops_unpack[d].clear();
+      c->n_same[d] = c->n_diff[d] = c->n_bc[d] = 0;
+   }
+   for (int a = 0; a < nb; a++) {
+      const mamr_block &b = c->blocks[a];
+      const int n = b.slot;
+      for (int l = 0; l < 6; l++) {
+         const int d = l/2, nl = b.nei_level[l];
+         if (nl == b.level) {
+            const int m = b.nei[l][0][0];
+            if (m > n) {
+               if (m >= c->p.max_blocks || slot2idx[m] < 0)
+                  return fail(MAMR_ETOPOLOGY, "ERROR: misconnected block (slot %d face %d -> %d)", n, l, m);
+               if (l%2 == 0) add_same(c, d, m, n);
+               else add_same(c, d, n, m);
+               c->n_same[d] += 2;
+            }
+         } else if (nl == b.level + 1) {
+            for (int i = 0; i < 2; i++)
+               for (int j = 0; j < 2; j++) {
+                  const int m = b.nei[l][i][j];
+                  if (m > n) {
+                     if (m >= c->p.max_blocks || slot2idx[m] < 0)
+                        return fail(MAMR_ETOPOLOGY, "ERROR: misconnected block (slot %d face %d -> %d)", n, l, m);
+                     add_diff(c, n, m, l, i, j);
+                     c->n_diff[d] += 2;
+                  }
+               }
+         } else if (nl == b.level - 1) {
+            const int m = b.nei[l][0][0];
+            if (m > n) {
+               if (m >= c->p.max_blocks || slot2idx[m] < 0)
+                  return fail(MAMR_ETOPOLOGY, "ERROR: misconnected block (slot %d face %d -> %d)", n, l, m);
+               const int k = 2*d + 1 - l%2;
+               const mamr_block &cb = c->blocks[slot2idx[m]];
+               for (int i = 0; i < 2; i++)
+                  for (int j = 0; j < 2; j++)
+                     if (cb.nei[k][i][j] == n) {
+                        add_diff(c, m, n, k, i, j);
+                        c->n_diff[d] += 2;
+                     }
+            }
+         } else if (nl == -2) {
+            add_bc(c, n, l);
+            c->n_bc[d] += 1;
+         } else
+            return fail(MAMR_ETOPOLOGY, "ERROR: misconnected block (slot %d face %d level %d nei_level %d)",
+                        n, l, b.level, nl);
+      }
+   }
+   // off-rank faces: pack + unpack descriptors from the comm lists
+   c->have_partners = false;
+   for (int d = 0; d < 3; d++) {
+      const DirLists &L = c->cl[d];
+      size_t smax = 0, rmax = 0;
+      for (size_t i = 0; i < L.partner.size(); i++) {
+         c->have_partners = true;
+         for (int f = L.index[i]; f < L.index[i] + L.num[i]; f++) {
+            add_pack(c, d, L.block[f], L.face_case[f], L.send_off[f]);
+            add_unpack(c, d, L.block[f], L.face_case[f], L.recv_off[f]);
+         }
+         smax = std::max(smax, (size_t)L.send_off[L.index[i]] + (size_t)L.send_size[i]);
+         rmax = std::max(rmax, (size_t)L.recv_off[L.index[i]] + (size_t)L.recv_size[i]);
+      }
+      if (smax > c->send_cap[d]) {
+         if (c->d_send[d]) CU(cudaFree(c->d_send[d]));
+         CU(cudaMalloc(&c->d_send[d], smax*sizeof(double)));
+         CU(cudaMemsetAsync(c->d_send[d], 0, smax*sizeof(double), c->stream));
+         c->send_cap[d] = smax;
+      }
+      if (rmax > c->recv_cap[d]) {
+         if (c->d_recv[d]) CU(cudaFree(c->d_recv[d]));
+         CU(cudaMalloc(&c->d_recv[d], rmax*sizeof(double)));
+         CU(cudaMemsetAsync(c->d_recv[d], 0, rmax*sizeof(double), c->stream));
+         c->recv_cap[d] = rmax;
+      }
+   }
+   // upload
+   size_t total = 0;
+   for (int d = 0; d < 3; d++) total += c->ops_main[d].size() + c->ops_unpack[d].size();
+   if (total > c->ops_cap) {
+      CU(cudaStreamSynchronize(c->stream));
+      if (c->d_ops) CU(cudaFree(c->d_ops));
+      c->ops_cap = total + total/4 + 64;
+      CU(cudaMalloc(&c->d_ops, c->ops_cap*sizeof(FaceOp)));
+   }
+   std::vector<FaceOp> all;
+   all.reserve(total);
+   for (int d = 0; d < 3; d++) {
+      c->off_main[d] = all.size();
+      all.insert(all.end(), c->ops_main[d].begin(), c->ops_main[d].end());
+   }
+   for (int d = 0; d < 3; d++) {
+      c->off_unpack[d] = all.size();
+      all.insert(all.end(), c->ops_unpack[d].begin(), c->ops_unpack[d].end());
+   }
+   if (total) {
+      // the previous descriptors may still be in use by queued launches
+      CU(cudaStreamSynchronize(c->stream));
+      CU(cudaMemcpyAsync(c->d_ops, all.data(), total*sizeof(FaceOp), cudaMemcpyHostToDevice,
+                         c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+   }
+   c->ops_dirty = false;
+   return MAMR_OK;
+}
+
+int flush_pending(mamr_ctx *c)
+{
+   if (c->pend_num > 0) {
+      {
+         KTimer t(c, KC_STENCIL);
+         launch_stencil(c->pool, c->g, c->d_slots, c->num_active, c->pend_start, c->pend_num,
+                        c->p.stencil, c->stream);
+      }
+      if (c->num_active > 0) c->cnt.kernel_launches++;
+      c->pend_num = 0;
+      CU(cudaGetLastError());
+   }
+   return MAMR_OK;
+}
+
+int check_slot(mamr_ctx *c, int slot)
+{
+   if (!c) return fail(MAMR_EINVAL, "null context");
+   if (slot < 0 || slot >= c->p.max_blocks)
+      return fail(MAMR_EINVAL, "slot %d out of range [0,%d)", slot, c->p.max_blocks);
+   return MAMR_OK;
+}
+
+void touch_all(mamr_ctx *c)
+{
+   std::fill(c->cs_valid.begin(), c->cs_valid.end(), 0);
+   c->modified_since_cs = true;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mamr_abi_version(void) { return MAMR_ABI_VERSION; }
+
+const char *mamr_last_error(void) { return g_err.c_str(); }
+
+int mamr_create(const mamr_params *params, mamr_ctx **out)
+{
+   if (!params || !out) return fail(MAMR_EINVAL, "null argument");
+   const mamr_params &p = *params;
+   // main.c:657-723 check_input, the parts this path depends on
+   if (p.nx <= 0 || p.ny <= 0 || p.nz <= 0 || (p.nx & 1) || (p.ny & 1) || (p.nz & 1))
+      return fail(MAMR_EINVAL, "block size must be even and > 0 (main.c:673-684)");
+   if (p.num_vars <= 0) return fail(MAMR_EINVAL, "num_vars must be > 0");
+   if (p.max_blocks <= 0) return fail(MAMR_EINVAL, "max_blocks must be > 0");
+   if (p.stencil != 7 && p.stencil != 27)
+      return fail(MAMR_EUNSUPPORTED, "--stencil %d: only 7 and 27 are on the device path", p.stencil);
+   if (p.code != 0)
+      return fail(MAMR_EUNSUPPORTED, "--code %d: only the minimal-send mode 0 is on the device path", p.code);
+   if (p.num_ranks < 1 || p.rank < 0 || p.rank >= p.num_ranks)
+      return fail(MAMR_EINVAL, "bad rank %d of %d", p.rank, p.num_ranks);
+   int ndev = 0;
+   cudaError_t e = cudaGetDeviceCount(&ndev);
+   if (e != cudaSuccess || ndev == 0)
+      return fail(MAMR_ECUDA, "no CUDA device (%s): miniamr_b200 has no CPU fallback",
+                  e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+   if (p.device >= 0) CU(cudaSetDevice(p.device));
+
+   mamr_ctx *c = new mamr_ctx();
+   c->p = p;
+   c->comm_vars = (p.comm_vars <= 0 || p.comm_vars > p.num_vars) ? p.num_vars : p.comm_vars;
+   Geometry &g = c->g;
+   g.n[0] = p.nx; g.n[1] = p.ny; g.n[2] = p.nz;
+   g.str[2] = 1; g.str[1] = p.nz + 2; g.str[0] = (p.ny + 2)*(p.nz + 2);
+   g.tile = (p.nx + 2)*g.str[0];
+   g.tile_stride = ((long long)g.tile + 15)/16*16;
+   g.var_stride = g.tile_stride*p.max_blocks;
+   memset(&c->cnt, 0, sizeof c->cnt);
+   c->cs_valid.assign(p.num_vars, 0);
+   c->cs_cache.assign(p.num_vars, 0.0);
+   std::string err;
+   if (!stencil_configure(g, err)) {
+      delete c;
+      return fail(MAMR_EUNSUPPORTED, "%s", err.c_str());
+   }
+#define CUC(call)                                                                         \
+   do {                                                                                   \
+      cudaError_t e_ = (call);                                                            \
+      if (e_ != cudaSuccess) {                                                            \
+         int r_ = fail(MAMR_ECUDA, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_),    \
+                       __FILE__, __LINE__, cudaGetErrorString(e_));                       \
+         mamr_destroy(c);                                                                 \
+         return r_;                                                                       \
+      }                                                                                   \
+   } while (0)
+   CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+   c->pool_bytes = (size_t)g.var_stride*p.num_vars*sizeof(double);
+   CUC(cudaMalloc(&c->pool, c->pool_bytes));
+   CUC(cudaMemsetAsync(c->pool, 0, c->pool_bytes, c->stream));
+   CUC(cudaMalloc(&c->d_sums, p.num_vars*sizeof(double)));
+   CUC(cudaMallocHost(&c->h_sums, p.num_vars*sizeof(double)));
+   CUC(cudaMalloc(&c->d_rops, c->rops_cap*sizeof(RefineOp)));
+   CUC(cudaMalloc(&c->d_payload, (size_t)p.num_vars*p.nx*p.ny*p.nz*sizeof(double)));
+   CUC(cudaMallocHost(&c->h_stage, (size_t)p.num_vars*g.tile*sizeof(double)));
+   CUC(cudaEventCreate(&c->ev_begin));
+   CUC(cudaEventCreate(&c->ev_end));
+   CUC(cudaStreamSynchronize(c->stream));
+#undef CUC
+   *out = c;
+   return MAMR_OK;
+}
+
+void mamr_destroy(mamr_ctx *c)
+{
+   if (!c) return;
+   if (c->stream) cudaStreamSynchronize(c->stream);
+   drain_ktimers(c);
+   for (cudaEvent_t e : c->ev_free) cudaEventDestroy(e);
+   if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
+   cudaFree(c->pool);
+   cudaFree(c->d_slots);
+   cudaFree(c->d_ops);
+   for (int d = 0; d < 3; d++) { cudaFree(c->d_send[d]); cudaFree(c->d_recv[d]); }
+   cudaFree(c->d_partials);
+   cudaFree(c->d_sums);
+   if (c->h_sums) cudaFreeHost(c->h_sums);
+   cudaFree(c->d_rops);
+   cudaFree(c->d_payload);
+   if (c->h_stage) cudaFreeHost(c->h_stage);
+   if (c->ev_begin) cudaEventDestroy(c->ev_begin);
+   if (c->ev_end) cudaEventDestroy(c->ev_end);
+   if (c->stream) cudaStreamDestroy(c->stream);
+   delete c;
+}
+
+int mamr_sync(mamr_ctx *c)
+{
+   if (!c) return fail(MAMR_EINVAL, "null context");
+   CK(flush_pending(c));
+   CU(cudaStreamSynchronize(c->stream));
+   return MAMR_OK;
+}
+
+int mamr_get_counters(mamr_ctx *c, mamr_counters *out)
+{
+   if (!c || !out) return fail(MAMR_EINVAL, "null argument");
+   *out = c->cnt;
+   return MAMR_OK;
+}
+
+int mamr_reset_counters(mamr_ctx *c)
+{
+   if (!c) return fail(MAMR_EINVAL, "null context");
+   memset(&c->cnt, 0, sizeof c->cnt);
+   return MAMR_OK;
+}
+
+long long mamr_tile_doubles(mamr_ctx *c) { return c ? c->g.tile : 0; }
+long long mamr_pool_bytes(mamr_ctx *c) { return c ? (long long)c->pool_bytes : 0; }
+
+void *mamr_pool_device_ptr(mamr_ctx *c, long long *var_stride, long long *slot_stride)
+{
+   if (!c) return nullptr;
+   if (var_stride) *var_stride = c->g.var_stride;
+   if (slot_stride) *slot_stride = c->g.tile_stride;
+   return c->pool;
+}
+
+// ---- block data in / out ---------------------------------------------------
+int mamr_upload_block(mamr_ctx *c, int slot, const double *tiles)
+{
+   CK(check_slot(c, slot));
+   if (!tiles) return fail(MAMR_EINVAL, "null tiles");
+   CK(flush_pending(c));
+   const Geometry &g = c->g;
+   CU(cudaMemcpy2DAsync(c->pool + tile_base(g, slot), g.var_stride*sizeof(double), tiles,
+                        g.tile*sizeof(double), g.tile*sizeof(double), c->p.num_vars,
+                        cudaMemcpyHostToDevice, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   touch_all(c);
+   return MAMR_OK;
+}
+
+int mamr_download_block(mamr_ctx *c, int slot, double *tiles)
+{
+   CK(check_slot(c, slot));
+   if (!tiles) return fail(MAMR_EINVAL, "null tiles");
+   CK(flush_pending(c));
+   const Geometry &g = c->g;
+   CU(cudaMemcpy2DAsync(tiles, g.tile*sizeof(double), c->pool + tile_base(g, slot),
+                        g.var_stride*sizeof(double), g.tile*sizeof(double), c->p.num_vars,
+                        cudaMemcpyDeviceToHost, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   return MAMR_OK;
+}
+
+int mamr_upload_tile(mamr_ctx *c, int slot, int var, const double *tile)
+{
+   CK(check_slot(c, slot));
+   if (var < 0 || var >= c->p.num_vars || !tile) return fail(MAMR_EINVAL, "bad var %d", var);
+   CK(flush_pending(c));
+   const Geometry &g = c->g;
+   CU(cudaMemcpyAsync(c->pool + (long long)var*g.var_stride + tile_base(g, slot), tile,
+                      g.tile*sizeof(double), cudaMemcpyHostToDevice, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   c->cs_valid[var] = 0;
+   c->modified_since_cs = true;
+   return MAMR_OK;
+}
+
+int mamr_download_tile(mamr_ctx *c, int slot, int var, double *tile)
+{
+   CK(check_slot(c, slot));
+   if (var < 0 || var >= c->p.num_vars || !tile) return fail(MAMR_EINVAL, "bad var %d", var);
+   CK(flush_pending(c));
+   const Geometry &g = c->g;
+   CU(cudaMemcpyAsync(tile, c->pool + (long long)var*g.var_stride + tile_base(g, slot),
+                      g.tile*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   return MAMR_OK;
+}
+
+int mamr_zero_block(mamr_ctx *c, int slot)
+{
+   CK(check_slot(c, slot));
+   CK(flush_pending(c));
+   const Geometry &g = c->g;
+   CU(cudaMemset2DAsync(c->pool + tile_base(g, slot), g.var_stride*sizeof(double), 0,
+                        g.tile*sizeof(double), c->p.num_vars, c->stream));
+   touch_all(c);
+   return MAMR_OK;
+}
+
+// ---- topology --------------------------------------------------------------
+int mamr_set_topology(mamr_ctx *c, int num_active, const mamr_block *sorted_blocks)
+{
+   if (!c || num_active < 0 || (num_active && !sorted_blocks))
+      return fail(MAMR_EINVAL, "bad topology arguments");
+   if (num_active > c->p.max_blocks)
+      return fail(MAMR_EINVAL, "num_active %d > max_blocks %d", num_active, c->p.max_blocks);
+   CK(flush_pending(c));
+   for (int a = 0; a < num_active; a++)
+      if (sorted_blocks[a].slot < 0 || sorted_blocks[a].slot >= c->p.max_blocks)
+         return fail(MAMR_EINVAL, "active block %d has slot %d out of range", a, sorted_blocks[a].slot);
+   c->blocks.assign(sorted_blocks, sorted_blocks + num_active);
+   c->num_active = num_active;
+   if ((size_t)num_active > c->slots_cap) {
+      CU(cudaStreamSynchronize(c->stream));
+      if (c->d_slots) CU(cudaFree(c->d_slots));
+      c->slots_cap = (size_t)num_active + num_active/4 + 64;
+      CU(cudaMalloc(&c->d_slots, c->slots_cap*sizeof(int)));
+   }
+   if ((size_t)num_active*c->p.num_vars > c->partials_cap) {
+      CU(cudaStreamSynchronize(c->stream));
+      if (c->d_partials) CU(cudaFree(c->d_partials));
+      c->partials_cap = c->slots_cap*c->p.num_vars;
+      CU(cudaMalloc(&c->d_partials, c->partials_cap*sizeof(double)));
+   }
+   std::vector<int> slots(num_active);
+   for (int a = 0; a < num_active; a++) slots[a] = sorted_blocks[a].slot;
+   CU(cudaStreamSynchronize(c->stream));
+   if (num_active)
+      CU(cudaMemcpyAsync(c->d_slots, slots.data(), num_active*sizeof(int),
+                         cudaMemcpyHostToDevice, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   c->ops_dirty = true;
+   touch_all(c);
+   return MAMR_OK;
+}
+
+int mamr_set_comm_lists(mamr_ctx *c, const mamr_comm_dir dirs[3])
+{
+   if (!c || !dirs) return fail(MAMR_EINVAL, "null argument");
+   CK(flush_pending(c));
+   for (int d = 0; d < 3; d++) {
+      const mamr_comm_dir &s = dirs[d];
+      DirLists &L = c->cl[d];
+      if (s.num_partners < 0 || s.num_cases < 0) return fail(MAMR_EINVAL, "negative list length");
+      L.partner.assign(s.partner, s.partner + s.num_partners);
+      L.index.assign(s.index, s.index + s.num_partners);
+      L.num.assign(s.num, s.num + s.num_partners);
+      L.send_size.assign(s.send_size, s.send_size + s.num_partners);
+      L.recv_size.assign(s.recv_size, s.recv_size + s.num_partners);
+      L.block.assign(s.block, s.block + s.num_cases);
+      L.face_case.assign(s.face_case, s.face_case + s.num_cases);
+      L.send_off.assign(s.send_off, s.send_off + s.num_cases);
+      L.recv_off.assign(s.recv_off, s.recv_off + s.num_cases);
+      for (int i = 0; i < s.num_partners; i++) {
+         if (L.partner[i] < 0 || L.partner[i] >= c->p.num_ranks || L.partner[i] == c->p.rank)
+            return fail(MAMR_EINVAL, "dir %d partner %d is not a valid peer rank", d, L.partner[i]);
+         if (L.index[i] < 0 || L.index[i] + L.num[i] > s.num_cases)
+            return fail(MAMR_EINVAL, "dir %d partner %d face range out of bounds", d, i);
+      }
+      for (int f = 0; f < s.num_cases; f++)
+         if (L.block[f] < 0 || L.block[f] >= c->p.max_blocks)
+            return fail(MAMR_EINVAL, "dir %d face %d slot out of range", d, f);
+   }
+   c->ops_dirty = true;
+   return MAMR_OK;
+}
+
+// ---- the stage hot path ----------------------------------------------------
+int mamr_comm(mamr_ctx *c, int start, int num_comm, int stage)
+{
+   if (!c) return fail(MAMR_EINVAL, "null context");
+   if (start < 0 || num_comm < 0 || start + num_comm > c->p.num_vars)
+      return fail(MAMR_EINVAL, "comm: bad variable range [%d,%d)", start, start + num_comm);
+   CK(flush_pending(c));
+   if (c->ops_dirty) CK(build_ops(c));
+   if (c->have_partners && !c->nccl)
+      return fail(MAMR_ENCCL, "comm: off-rank partners present but mamr_nccl_init was not called");
+   static const int perm[6][3] = { {0, 1, 2}, {1, 2, 0}, {2, 0, 1}, {0, 2, 1}, {1, 0, 2}, {2, 1, 0} };
+   for (int o = 0; o < 3; o++) {
+      const int d = c->p.permute ? perm[((stage%6) + 6)%6][o] : o;   // comm.c:51-55
+      const DirLists &L = c->cl[d];
+      if (!c->ops_main[d].empty() && num_comm > 0) {
+         KTimer t(c, KC_GHOST);
+         launch_ghost(c->d_ops + c->off_main[d], (int)c->ops_main[d].size(), c->pool,
+                      c->d_send[d], c->d_recv[d], c->g.var_stride, start, num_comm, c->stream);
+         c->cnt.kernel_launches++;
+      }
+      if (!L.partner.empty()) {
+         // one message per (direction, partner), comm.c:71-84 / 120-151
+         NC(g_nccl.GroupStart());
+         for (size_t i = 0; i < L.partner.size(); i++) {
+            NC(g_nccl.Recv(c->d_recv[d] + L.recv_off[L.index[i]], (size_t)L.recv_size[i],
+                           NCCL_DOUBLE, L.partner[i], c->nccl, c->stream));
+            NC(g_nccl.Send(c->d_send[d] + L.send_off[L.index[i]], (size_t)L.send_size[i],
+                           NCCL_DOUBLE, L.partner[i], c->nccl, c->stream));
+            c->cnt.counter_halo_recv[d]++;
+            c->cnt.counter_halo_send[d]++;
+            c->cnt.size_mesg_recv[d] += (double)L.recv_size[i]*sizeof(double);
+            c->cnt.size_mesg_send[d] += (double)L.send_size[i]*sizeof(double);
+            c->cnt.counter_face_send[d] += L.num[i];
+            c->cnt.counter_face_recv[d] += L.num[i];
+         }
+         NC(g_nccl.GroupEnd());
+         if (!c->ops_unpack[d].empty() && num_comm > 0) {
+            KTimer t(c, KC_GHOST);
+            launch_ghost(c->d_ops + c->off_unpack[d], (int)c->ops_unpack[d].size(), c->pool,
+                         c->d_send[d], c->d_recv[d], c->g.var_stride, start, num_comm,
+                         c->stream);
+            c->cnt.kernel_launches++;
+         }
+      }
+      c->cnt.counter_same[d] += c->n_same[d];
+      c->cnt.counter_diff[d] += c->n_diff[d];
+      c->cnt.counter_bc[d] += c->n_bc[d];
+   }
+   CU(cudaGetLastError());
+   return MAMR_OK;
+}
+
+int mamr_stencil_vars(mamr_ctx *c, int var_start, int num)
+{
+   if (!c) return fail(MAMR_EINVAL, "null context");
+   if (var_start < 0 || num < 0 || var_start + num > c->p.num_vars)
+      return fail(MAMR_EINVAL, "stencil: bad variable range [%d,%d)", var_start, var_start + num);
+   if (num == 0) return MAMR_OK;
+   // defer: consecutive variables are merged into one launch (driver.c:85-86
+   // calls the stencil once per variable)
+   if (c->pend_num > 0 && var_start == c->pend_start + c->pend_num)
+      c->pend_num += num;
+   else {
+      CK(flush_pending(c));
+      c->pend_start = var_start;
+      c->pend_num = num;
+   }
+   for (int v = var_start; v < var_start + num; v++) c->cs_valid[v] = 0;
+   c->modified_since_cs = true;
+   // stencil.c:100-101, 142-143
+   const double cells = (double)c->num_active*c->p.nx*c->p.ny*c->p.nz;
+   c->cnt.total_fp_divs += cells*num;
+   c->cnt.total_fp_adds += (c->p.stencil == 7 ? 6.0 : 26.0)*cells*num;
+   return MAMR_OK;
+}
+
+int mamr_stencil_driver(mamr_ctx *c, int var, int calc_stage)
+{
+   (void)calc_stage;   // only selects the kernel for --stencil 0 (stencil.c:48-70)
+   return mamr_stencil_vars(c, var, 1);
+}
+
+int mamr_stencil_calc(mamr_ctx *c, int var) { return mamr_stencil_vars(c, var, 1); }
+
+int mamr_check_sum_vars(mamr_ctx *c, int var_start, int num, double *sums)
+{
+   if (!c || !sums) return fail(MAMR_EINVAL, "null argument");
+   if (var_start < 0 || num <= 0 || var_start + num > c->p.num_vars)
+      return fail(MAMR_EINVAL, "check_sum: bad variable range [%d,%d)", var_start, var_start + num);
+   CK(flush_pending(c));
+   {
+      KTimer t(c, KC_CHECKSUM);
+      launch_checksum(c->pool, c->g, c->d_slots, c->num_active, var_start, num, c->d_partials,
+                      c->d_sums, c->stream);
+   }
+   c->cnt.kernel_launches += c->num_active > 0 ? 2 : 1;
+   CU(cudaGetLastError());
+   if (c->p.num_ranks > 1) {
+      if (!c->nccl) return fail(MAMR_ENCCL, "check_sum: mamr_nccl_init was not called");
+      NC(g_nccl.AllReduce(c->d_sums, c->d_sums, (size_t)num, NCCL_DOUBLE, NCCL_SUM, c->nccl,
+                          c->stream));   // check_sum.c:57
+   }
+   CU(cudaMemcpyAsync(c->h_sums, c->d_sums, num*sizeof(double), cudaMemcpyDeviceToHost,
+                      c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   for (int i = 0; i < num; i++) {
+      sums[i] = c->h_sums[i];
+      c->cs_cache[var_start + i] = c->h_sums[i];
+      c->cs_valid[var_start + i] = 1;
+   }
+   c->modified_since_cs = false;
+   return MAMR_OK;
+}
+
+int mamr_check_sum(mamr_ctx *c, int var, double *sum)
+{
+   if (!c || !sum) return fail(MAMR_EINVAL, "null argument");
+   if (var < 0 || var >= c->p.num_vars) return fail(MAMR_EINVAL, "check_sum: bad var %d", var);
+   c->cnt.total_red++;   // check_sum.c:62
+   if (c->cs_valid[var] && c->pend_num == 0) {
+      *sum = c->cs_cache[var];
+      return MAMR_OK;
+   }
+   // init.c:681-682 asks for every variable back to back with no update in
+   // between: after the first such call compute the rest in one launch
+   int num = 1;
+   if (!c->modified_since_cs && c->pend_num == 0)
+      while (var + num < c->p.num_vars && !c->cs_valid[var + num]) num++;
+   std::vector<double> tmp(num);
+   CK(mamr_check_sum_vars(c, var, num, tmp.data()));
+   *sum = tmp[0];
+   return MAMR_OK;
+}
+
+int mamr_stage(mamr_ctx *c, int stage)
+{
+   if (!c) return fail(MAMR_EINVAL, "null context");
+   for (int start = 0; start < c->p.num_vars; start += c->comm_vars) {   // driver.c:75-89
+      const int number = std::min(c->comm_vars, c->p.num_vars - start);
+      CK(mamr_comm(c, start, number, stage));
+      CK(mamr_stencil_vars(c, start, number));
+   }
+   return MAMR_OK;
+}
+
+// ---- refinement / migration ------------------------------------------------
+static int push_rop(mamr_ctx *c, const RefineOp &op, RefineOp **d_out)
+{
+   if (c->rops_pos == c->rops_cap) {
+      CU(cudaStreamSynchronize(c->stream));
+      c->rops_pos = 0;
+   }
+   *d_out = c->d_rops + c->rops_pos++;
+   CU(cudaMemcpyAsync(*d_out, &op, sizeof op, cudaMemcpyHostToDevice, c->stream));
+   return MAMR_OK;
+}
+
+int mamr_split_block(mamr_ctx *c, int parent_slot, const int child_slots[8])
+{
+   CK(check_slot(c, parent_slot));
+   RefineOp op;
+   op.parent = parent_slot;
+   for (int o = 0; o < 8; o++) {
+      CK(check_slot(c, child_slots[o]));
+      if (child_slots[o] == parent_slot) return fail(MAMR_EINVAL, "split: child slot equals parent");
+      op.child[o] = child_slots[o];
+   }
+   CK(flush_pending(c));
+   RefineOp *d;
+   CK(push_rop(c, op, &d));
+   launch_split(c->pool, c->g, d, 1, c->p.num_vars, c->stream);
+   c->cnt.kernel_launches++;
+   CU(cudaGetLastError());
+   touch_all(c);
+   return MAMR_OK;
+}
+
+int mamr_consolidate_block(mamr_ctx *c, const int child_slots[8], int parent_slot)
+{
+   CK(check_slot(c, parent_slot));
+   RefineOp op;
+   op.parent = parent_slot;
+   for (int o = 0; o < 8; o++) {
+      CK(check_slot(c, child_slots[o]));
+      if (child_slots[o] == parent_slot) return fail(MAMR_EINVAL, "consolidate: child slot equals parent");
+      op.child[o] = child_slots[o];
+   }
+   CK(flush_pending(c));
+   RefineOp *d;
+   CK(push_rop(c, op, &d));
+   launch_consolidate(c->pool, c->g, d, 1, c->p.num_vars, c->stream);
+   c->cnt.kernel_launches++;
+   CU(cudaGetLastError());
+   touch_all(c);
+   return MAMR_OK;
+}
+
+int mamr_pack_block(mamr_ctx *c, int slot, double *payload)
+{
+   CK(check_slot(c, slot));
+   if (!payload) return fail(MAMR_EINVAL, "null payload");
+   CK(flush_pending(c));
+   const size_t n = (size_t)c->p.num_vars*c->p.nx*c->p.ny*c->p.nz;
+   launch_pack_block(c->pool, c->g, slot, c->p.num_vars, c->d_payload, c->stream);
+   c->cnt.kernel_launches++;
+   CU(cudaMemcpyAsync(payload, c->d_payload, n*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   c->cnt.migrate_bytes += (double)n*sizeof(double);
+   return MAMR_OK;
+}
+
+int mamr_unpack_block(mamr_ctx *c, int slot, const double *payload)
+{
+   CK(check_slot(c, slot));
+   if (!payload) return fail(MAMR_EINVAL, "null payload");
+   CK(flush_pending(c));
+   const size_t n = (size_t)c->p.num_vars*c->p.nx*c->p.ny*c->p.nz;
+   CU(cudaMemcpyAsync(c->d_payload, payload, n*sizeof(double), cudaMemcpyHostToDevice, c->stream));
+   launch_unpack_block(c->pool, c->g, slot, c->p.num_vars, c->d_payload, c->stream);
+   c->cnt.kernel_launches++;
+   CU(cudaStreamSynchronize(c->stream));
+   touch_all(c);
+   return MAMR_OK;
+}
+
+int mamr_send_block(mamr_ctx *c, int slot, int dest_rank)
+{
+   CK(check_slot(c, slot));
+   if (!c->nccl) return fail(MAMR_ENCCL, "send_block: mamr_nccl_init was not called");
+   if (dest_rank < 0 || dest_rank >= c->p.num_ranks || dest_rank == c->p.rank)
+      return fail(MAMR_EINVAL, "send_block: bad destination rank %d", dest_rank);
+   CK(flush_pending(c));
+   const size_t n = (size_t)c->p.num_vars*c->p.nx*c->p.ny*c->p.nz;
+   launch_pack_block(c->pool, c->g, slot, c->p.num_vars, c->d_payload, c->stream);
+   c->cnt.kernel_launches++;
+   NC(g_nccl.Send(c->d_payload, n, NCCL_DOUBLE, dest_rank, c->nccl, c->stream));
+   c->cnt.migrate_bytes += (double)n*sizeof(double);
+   CU(cudaGetLastError());
+   return MAMR_OK;
+}
+
+int mamr_recv_block(mamr_ctx *c, int slot, int src_rank)
+{
+   CK(check_slot(c, slot));
+   if (!c->nccl) return fail(MAMR_ENCCL, "recv_block: mamr_nccl_init was not called");
+   if (src_rank < 0 || src_rank >= c->p.num_ranks || src_rank == c->p.rank)
+      return fail(MAMR_EINVAL, "recv_block: bad source rank %d", src_rank);
+   CK(flush_pending(c));
+   const size_t n = (size_t)c->p.num_vars*c->p.nx*c->p.ny*c->p.nz;
+   NC(g_nccl.Recv(c->d_payload, n, NCCL_DOUBLE, src_rank, c->nccl, c->stream));
+   launch_unpack_block(c->pool, c->g, slot, c->p.num_vars, c->d_payload, c->stream);
+   c->cnt.kernel_launches++;
+   CU(cudaGetLastError());
+   touch_all(c);
+   return MAMR_OK;
+}
+
+// ---- multi-GPU -------------------------------------------------------------
+int mamr_nccl_get_unique_id(char id[MAMR_NCCL_ID_BYTES])
+{
+   if (!id) return fail(MAMR_EINVAL, "null id");
+   if (!load_nccl()) return fail(MAMR_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
+   ncclUniqueId u;
+   NC(g_nccl.GetUniqueId(&u));
+   memcpy(id, u.internal, MAMR_NCCL_ID_BYTES);
+   return MAMR_OK;
+}
+
+int mamr_nccl_init(mamr_ctx *c, const char id[MAMR_NCCL_ID_BYTES])
+{
+   if (!c || !id) return fail(MAMR_EINVAL, "null argument");
+   if (!load_nccl()) return fail(MAMR_ENCCL, "cannot load libnccl.so.2: %s", dlerror());
+   ncclUniqueId u;
+   memcpy(u.internal, id, MAMR_NCCL_ID_BYTES);
+   NC(g_nccl.CommInitRank(&c->nccl, c->p.num_ranks, u, c->p.rank));
+   return MAMR_OK;
+}
+
+// ---- measurement -----------------------------------------------------------
+int mamr_timer_begin(mamr_ctx *c)
+{
+   if (!c) return fail(MAMR_EINVAL, "null context");
+   CK(flush_pending(c));
+   CU(cudaEventRecord(c->ev_begin, c->stream));
+   return MAMR_OK;
+}
+
+int mamr_timer_end(mamr_ctx *c, float *ms)
+{
+   if (!c || !ms) return fail(MAMR_EINVAL, "null argument");
+   CK(flush_pending(c));
+   CU(cudaEventRecord(c->ev_end, c->stream));
+   CU(cudaEventSynchronize(c->ev_end));
+   CU(cudaEventElapsedTime(ms, c->ev_begin, c->ev_end));
+   return MAMR_OK;
+}
+
+int mamr_kernel_timing(mamr_ctx *c, int enable)
+{
+   if (!c) return fail(MAMR_EINVAL, "null context");
+   CK(flush_pending(c));
+   CU(cudaStreamSynchronize(c->stream));
+   drain_ktimers(c);
+   c->ktiming = enable != 0;
+   for (int i = 0; i < 3; i++) { c->k_ms[i] = 0; c->k_launches[i] = 0; }
+   return MAMR_OK;
+}
+
+int mamr_kernel_time_ms(mamr_ctx *c, float *stencil_ms, float *ghost_ms, float *checksum_ms,
+                        long long *stencil_launches, long long *ghost_launches,
+                        long long *checksum_launches)
+{
+   if (!c) return fail(MAMR_EINVAL, "null context");
+   CK(flush_pending(c));
+   CU(cudaStreamSynchronize(c->stream));
+   drain_ktimers(c);
+   if (stencil_ms) *stencil_ms = (float)c->k_ms[KC_STENCIL];
+   if (ghost_ms) *ghost_ms = (float)c->k_ms[KC_GHOST];
+   if (checksum_ms) *checksum_ms = (float)c->k_ms[KC_CHECKSUM];
+   if (stencil_launches) *stencil_launches = c->k_launches[KC_STENCIL];
+   if (ghost_launches) *ghost_launches = c->k_launches[KC_GHOST];
+   if (checksum_launches) *checksum_launches = c->k_launches[KC_CHECKSUM];
+   return MAMR_OK;
+}
+
+}  // extern "C"

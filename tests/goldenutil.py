@@ -1,0 +1,40 @@
+"""Load tests/golden/*.npz (made by tests/golden/make_golden.py from the reference)."""
+import glob
+import hashlib
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+NAMES = sorted(os.path.splitext(os.path.basename(p))[0]
+               for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+class Golden:
+    def __init__(self, name):
+        z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+        self.name = name
+        self.args = str(z["args"])
+        self.seed = int(z["seed"])
+        self.stages = int(z["stages"])
+        (self.nx, self.ny, self.nz, self.num_vars, self.comm_vars, self.max_blocks,
+         self.stencil, self.permute) = (int(x) for x in z["params"])
+        self.slots, self.level = z["slots"], z["level"]
+        self.nei_level, self.nei = z["nei_level"], z["nei"]
+        self.check_sums = z["check_sums"]
+        self.sha256 = str(z["sha256"])
+        self.tile_shape = (self.nx + 2, self.ny + 2, self.nz + 2)
+
+    def seeded_blocks(self):
+        """Yield (slot, tiles[num_vars, nx+2, ny+2, nz+2]) exactly as make_golden seeded them."""
+        rs = np.random.RandomState(self.seed)
+        shape = (self.num_vars,) + self.tile_shape
+        for s in self.slots:
+            yield int(s), rs.random_sample(shape)
+
+
+def digest(blocks):
+    h = hashlib.sha256()
+    for b in blocks:
+        h.update(np.ascontiguousarray(b, np.float64).tobytes())
+    return h.hexdigest()

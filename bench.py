@@ -1,0 +1,417 @@
+#!/usr/bin/env python
+"""bench.py — cell-var updates/s of the miniAMR stencil+ghost stage on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one stage of driver.c:73-89 over the whole mesh: comm() for every
+group of comm_vars variables followed by stencil_driver() for each of them.
+Workload (BASELINE.json configs[1]): uniform mesh of 16x16x16-cell blocks, 40
+variables, 27-point stencil, reflective domain boundary; 16^3 = 4096 blocks
+(7.6 GB of block data, >> the 126 MB L2) per GPU.  With N > 1 every rank owns
+such a sub-cube of an npx x npy x npz rank grid (weak scaling) and the faces
+between ranks travel by NCCL send/recv, one message per direction and partner
+as in comm.c:71-84/120-151.
+
+One JSON line is printed by rank 0 (see DESIGN.md "Measurement" for every key).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "cell-var updates/s, stencil+ghost stage"
+UNIT = "cell-var updates/s"
+
+WORKLOADS = {
+    # name: nx, num_vars, stencil, blocks per edge per GPU
+    "cfg2": dict(n=16, num_vars=40, stencil=27, bpd=16,
+                 desc="BASELINE configs[1]: uniform 16^3-cell blocks, 40 vars, 27-pt"),
+    "cfg3": dict(n=32, num_vars=40, stencil=7, bpd=8,
+                 desc="BASELINE configs[2]: uniform 32^3-cell blocks, 40 vars, 7-pt"),
+    "cfg1u": dict(n=10, num_vars=40, stencil=7, bpd=16,
+                  desc="10^3-cell blocks, 40 vars, 7-pt (configs[0] shape, uniform mesh)"),
+}
+
+
+def halo_cells(n, stencil):
+    return 6*n*n if stencil == 7 else (n + 2)**3 - n**3
+
+
+def bytes_per_update(n, stencil):
+    """stage B = 16 + 24 H/n^3; stencil kernel 16 + 8 H/n^3;
+    ghost kernels 16 H/n^3."""
+    h = halo_cells(n, stencil)/float(n**3)
+    return dict(stage=16 + 24*h, stencil=16 + 8*h, ghost=16*h)
+
+
+def rank_grid(n):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n]
+
+
+# ---------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md)
+# ---------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv", prefix="clocks_")
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=fd,
+                stderr=subprocess.DEVNULL)
+            os.close(fd)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if not self.proc:
+            return out
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, f[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm)//2], sm_max_mhz=max(mx), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ---------------------------------------------------------------------------
+# reference CPU arm: the UNMODIFIED reference (oracle/_ref, openmp/ build) driven
+# stage by stage on the host cores
+# ---------------------------------------------------------------------------
+def cpu_reference(workload, steps, warmup, budget_s=None):
+    """Time `steps` stages (or as many as fit in budget_s) of the reference's own
+    comm()+stencil_driver() loop on a bounded sample of the workload."""
+    w = WORKLOADS[workload]
+    cores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    os.environ.setdefault("OMP_PROC_BIND", "spread")
+    from oracle import refharness
+    kind, variant = "reference", "omp"
+    if not refharness.available("omp"):
+        variant = "ref"
+        cores = 1
+    if not refharness.available(variant):
+        return None
+    n, V = w["n"], w["num_vars"]
+    R = 3 if n <= 16 else 2                   # 512 or 64 blocks: seconds per stage at most
+    nblocks = 8**R
+    args = (f"--nx {n} --ny {n} --nz {n} --num_vars {V} --stencil {w['stencil']} "
+            f"--uniform_refine 1 --num_refine {R} --max_blocks {nblocks + 16}").split()
+    r = refharness.RefMiniAMR(args, variant=variant)
+    r.init()
+    r.refine(0)
+    assert r.p["num_active"] == nblocks, r.p
+    upd = float(nblocks)*n**3*V
+    for st in range(warmup):
+        r.stage(st)
+    times = []
+    t_all = time.perf_counter()
+    st = warmup
+    while True:
+        t0 = time.perf_counter()
+        r.stage(st)
+        times.append(time.perf_counter() - t0)
+        st += 1
+        if budget_s is None:
+            if len(times) >= steps:
+                break
+        elif (time.perf_counter() - t_all >= budget_s and len(times) >= 3) or len(times) >= 200:
+            break
+    total = sum(times)
+    return dict(value=upd*len(times)/total, unit=UNIT, cores=cores, kind=kind,
+                sample=(f"{len(times)} stages of {nblocks} blocks ({n}^3 cells, {V} vars, "
+                        f"{w['stencil']}-pt, uniform) = {upd*len(times):.3g} updates in {total:.2f} s; "
+                        f"unmodified reference {'openmp/' if variant == 'omp' else 'ref/'} build, "
+                        f"gcc -O3, OMP_NUM_THREADS={cores}"),
+                ms_per_step=1e3*total/len(times), steps=len(times))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_reference(args.workload, args.steps, args.warmup)
+    if res is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
+        return
+    w = WORKLOADS[args.workload]
+    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT,
+            "n_gpus": args.gpus, "steps": res["steps"], "warmup": args.warmup,
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic (rand() fill, init.c:484-495)",
+            "config": {"workload": f"{args.workload}: {w['desc']}",
+                       "sample": res["sample"]},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from miniamr_b200.capi import DeviceMesh
+    from miniamr_b200.mesh import uniform_mesh
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    w = WORKLOADS[args.workload]
+    n, V, stencil = w["n"], w["num_vars"], w["stencil"]
+    B = args.blocks or w["bpd"]
+    nblocks = B**3
+    npx, npy, npz = rank_grid(world)
+    top = uniform_mesh(B, B, B, npx, npy, npz, rank, n, n, n, comm_vars=V, stencil=stencil)
+    d = DeviceMesh(n, n, n, V, nblocks, stencil=stencil, device=local, rank=rank,
+                   num_ranks=world)
+    d.set_topology(top["slots"], top["level"], top["nei_level"], top["nei"])
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(DeviceMesh.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        d.nccl_init(bytes(uid.cpu().numpy().tobytes()))
+        d.set_comm_lists(top["dirs"])
+
+    # synthetic state in pinned host memory, pool layout [var][slot][tile]
+    tile = (n + 2)**3
+    host = torch.empty((V, nblocks, n + 2, n + 2, n + 2), dtype=torch.float64, pin_memory=True)
+    g = torch.Generator().manual_seed(1234 + rank)
+    chunk = torch.empty((nblocks, n + 2, n + 2, n + 2), dtype=torch.float64)
+    for v in range(V):
+        chunk.zero_()
+        chunk[:, 1:-1, 1:-1, 1:-1].uniform_(0.0, 1.0, generator=g)   # init.c:484-495 shape
+        host[v].copy_(chunk)
+    del chunk
+    h2d_bytes = host.numel()*8
+    d.upload_vars(0, V, nblocks, host.data_ptr())
+    d.sync()
+    sums0 = d.check_sum_vars(0, V)
+
+    upd_per_step = float(nblocks)*world*n**3*V
+    bpu = bytes_per_update(n, stencil)
+
+    def barrier():
+        d.sync()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: `value` -------------------------------------
+    for st in range(args.warmup):
+        d.stage(st)
+    barrier()
+    d.reset_counters()
+    d.kernel_timing(True)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    d.timer_begin()
+    for st in range(args.steps):
+        d.stage(args.warmup + st)
+    ms = d.timer_end()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    kt = d.kernel_times()
+    d.kernel_timing(False)
+    cnt = d.counters()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = upd_per_step*args.steps/(ms*1e-3)
+
+    # conservation (driver.c:96-101): the average with reflective boundaries keeps
+    # the per-variable sum
+    sums1 = d.check_sum_vars(0, V)
+    drift = float(np.max(np.abs(sums1 - sums0)/np.abs(sums0)))
+    if not drift < 1e-9:
+        raise SystemExit(f"bench.py: checksum drift {drift} exceeds the reference's tolerance")
+
+    # ---- end to end through the reference's call surface: `e2e` ----------------
+    # One job = the state uploaded from pinned host memory (what init.c:484-495
+    # hands over), then K stages issued exactly as driver.c:75-103 issues them
+    # (comm per group, stencil_driver per variable, check_sum per variable with
+    # its device->host read), all inside the timed region.
+    def e2e_job(steps, reupload_every_step):
+        barrier()
+        t0 = time.perf_counter()
+        d.timer_begin()
+        if not reupload_every_step:
+            d.upload_vars(0, V, nblocks, host.data_ptr())
+        for st in range(steps):
+            if reupload_every_step:
+                d.upload_vars(0, V, nblocks, host.data_ptr())
+            d.comm(0, V, st)
+            for v in range(V):
+                d.stencil_driver(v, st)
+            for v in range(V):
+                d.check_sum(v)
+        ms_ = d.timer_end()
+        barrier()
+        wall = (time.perf_counter() - t0)*1e3
+        ms_ = max(ms_, wall)          # host-side call overhead counts end to end
+        if world > 1:
+            t_ = torch.tensor([ms_], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            ms_ = float(t_.item())
+        return ms_
+
+    e2e_job(1, False)                                  # warm the path
+    e2e_ms = e2e_job(args.steps, False)
+    e2e_val = upd_per_step*args.steps/(e2e_ms*1e-3)
+    strict_steps = max(1, min(args.steps, 3))
+    strict_ms = e2e_job(strict_steps, True)
+    strict_val = upd_per_step*strict_steps/(strict_ms*1e-3)
+
+    line = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else \
+            "fallback (B200_PROFILING.md 6.65 TB/s)"
+        st_launch_ms = kt["stencil_ms"]/max(1, kt["stencil_launches"])
+        st_bytes = bpu["stencil"]*nblocks*n**3*V          # per launch, this rank
+        achieved = st_bytes/(st_launch_ms*1e-3)/1e9
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tr.get(f"{args.workload}:{B}", {}).get("stencil_bytes_per_launch")
+        except Exception:
+            pass
+        stage_gbs = value/world*bpu["stage"]/1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms/args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic (uniform random interiors, seed 1234+rank)",
+            "config": {"workload": f"{args.workload}: {w['desc']}",
+                       "blocks_per_gpu": nblocks, "cells_per_block": n**3, "num_vars": V,
+                       "stencil": stencil, "rank_grid": [npx, npy, npz],
+                       "bytes_per_gpu": d.pool_bytes(),
+                       "cache": "inputs (7.6 GB/GPU at the default size) exceed the 126 MB L2"},
+            "roofline": {"bound": "hbm", "kernel": f"stencil_kernel<{stencil}>",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved/peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": st_bytes,
+                         "launch_ms": st_launch_ms,
+                         "stage_bytes_per_update": bpu["stage"],
+                         "stage_achieved_gbs_per_gpu": stage_gbs,
+                         "stage_frac": stage_gbs/peak,
+                         "kernel_share_of_step": {
+                             "stencil": kt["stencil_ms"]/ms, "ghost": kt["ghost_ms"]/ms}},
+            "clocks": clk,
+            "e2e": {"value": e2e_val, "unit": UNIT,
+                    "h2d_bytes_per_step": h2d_bytes/args.steps,
+                    "d2h_bytes_per_step": 8*V,
+                    "what": (f"state uploaded once from pinned host memory ({h2d_bytes} B per GPU) + "
+                             f"{args.steps} stages through comm/stencil_driver/check_sum per "
+                             "variable (driver.c:75-103), checksums read back every stage"),
+                    "ms_total": e2e_ms,
+                    "reupload_every_step": {"value": strict_val, "steps": strict_steps,
+                                            "h2d_bytes_per_step": h2d_bytes,
+                                            "ms_per_step": strict_ms/strict_steps}},
+            "gpu_launches": int(cnt["kernel_launches"]),
+            "nvlink_bytes_per_step": (sum(cnt["size_mesg_send"])/args.steps if world > 1 else 0),
+            "checksum_drift": drift,
+        }
+    d.close()
+    del host
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cb = cpu_reference(args.workload, 0, 1, budget_s=args.cpu_seconds)
+                if cb:
+                    line["cpu_baseline"] = {k: cb[k] for k in
+                                            ("value", "unit", "cores", "kind", "sample")}
+            except Exception as e:   # the baseline never gates the bench line
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0,
+                                        "kind": "reference", "sample": f"failed: {e}"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--blocks", type=int, default=0, help="blocks per edge per GPU (default per workload)")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

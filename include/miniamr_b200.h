@@ -112,6 +112,11 @@ int mamr_download_block(mamr_ctx *ctx, int slot, double *tiles);
 int mamr_upload_tile(mamr_ctx *ctx, int slot, int var, const double *tile);
 int mamr_download_tile(mamr_ctx *ctx, int slot, int var, double *tile);
 int mamr_zero_block(mamr_ctx *ctx, int slot);
+/* bulk form for slots [0, num_slots): host[var - var_start][slot][tile], the
+ * layout of the pool without its tile padding.  Asynchronous when `host` is
+ * pinned memory: the buffer must stay valid until mamr_sync(). */
+int mamr_upload_vars(mamr_ctx *ctx, int var_start, int num, int num_slots, const double *host);
+int mamr_download_vars(mamr_ctx *ctx, int var_start, int num, int num_slots, double *host);
 
 /* ---- topology: what comm()/stencil_calc()/check_sum() read through the
  *      globals blocks[], sorted_list, sorted_index (block.h:36-77) and the

@@ -724,6 +724,42 @@ int mamr_zero_block(mamr_ctx *c, int slot)
    return MAMR_OK;
 }
 
+int mamr_upload_vars(mamr_ctx *c, int var_start, int num, int num_slots, const double *host)
+{
+   if (!c || !host) return fail(MAMR_EINVAL, "null argument");
+   if (var_start < 0 || num <= 0 || var_start + num > c->p.num_vars || num_slots <= 0 ||
+       num_slots > c->p.max_blocks)
+      return fail(MAMR_EINVAL, "upload_vars: bad range vars [%d,%d) slots %d", var_start,
+                  var_start + num, num_slots);
+   CK(flush_pending(c));
+   const Geometry &g = c->g;
+   for (int v = 0; v < num; v++)
+      CU(cudaMemcpy2DAsync(c->pool + (long long)(var_start + v)*g.var_stride,
+                           g.tile_stride*sizeof(double),
+                           host + (size_t)v*num_slots*g.tile, g.tile*sizeof(double),
+                           g.tile*sizeof(double), num_slots, cudaMemcpyHostToDevice, c->stream));
+   touch_all(c);
+   return MAMR_OK;
+}
+
+int mamr_download_vars(mamr_ctx *c, int var_start, int num, int num_slots, double *host)
+{
+   if (!c || !host) return fail(MAMR_EINVAL, "null argument");
+   if (var_start < 0 || num <= 0 || var_start + num > c->p.num_vars || num_slots <= 0 ||
+       num_slots > c->p.max_blocks)
+      return fail(MAMR_EINVAL, "download_vars: bad range vars [%d,%d) slots %d", var_start,
+                  var_start + num, num_slots);
+   CK(flush_pending(c));
+   const Geometry &g = c->g;
+   for (int v = 0; v < num; v++)
+      CU(cudaMemcpy2DAsync(host + (size_t)v*num_slots*g.tile, g.tile*sizeof(double),
+                           c->pool + (long long)(var_start + v)*g.var_stride,
+                           g.tile_stride*sizeof(double), g.tile*sizeof(double), num_slots,
+                           cudaMemcpyDeviceToHost, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   return MAMR_OK;
+}
+
 // ---- topology --------------------------------------------------------------
 int mamr_set_topology(mamr_ctx *c, int num_active, const mamr_block *sorted_blocks)
 {

@@ -120,10 +120,9 @@ def test_split_consolidate_pack_bit_exact(dims):
         assert (bits(d.download_block(s)) == bits(m.data[s])).all(), f"split slot {s}"
     d.consolidate_block(kids, 13); m.consolidate_block(kids, 13)
     assert (bits(d.download_block(13)) == bits(m.data[13])).all(), "consolidate"
-    # split followed by consolidate restores the parent's interior exactly? Not in general
-    # (x/8 summed 8 times is exact only for these power-of-two scalings) -- it is:
-    assert (bits(d.download_block(13)[:, 1:-1, 1:-1, 1:-1]) ==
-            bits(m.data[4][:, 1:-1, 1:-1, 1:-1])).all()
+    # (split then consolidate does not restore the parent bit for bit: 3*(p/8) rounds)
+    rel = np.abs(d.download_block(13)[:, 1:-1, 1:-1, 1:-1] - m.data[4][:, 1:-1, 1:-1, 1:-1])
+    assert (rel <= 4e-16*np.abs(m.data[4][:, 1:-1, 1:-1, 1:-1])).all()
     p = d.pack_block(7)
     assert (bits(p) == bits(m.pack_block(7))).all(), "pack_block payload"
     d.unpack_block(15, p); m.unpack_block(15, p)

@@ -13,6 +13,8 @@
  *     pool[var][slot][tile],  tile = (nx+2)(ny+2)(nz+2) doubles, k fastest,
  *     ghosts at index 0 and n+1 exactly like block.array[var][i][j][k]
  *     (block.h:52; allocation main.c:429-450), tile stride padded to 128 B.
+ * There are two such pools: a stage reads a variable from its current pool and
+ * writes the other one (comm + stencil fused in one pass), then they swap.
  * `slot` is the reference's index into blocks[] (0 <= slot < max_blocks).
  *
  * There is NO CPU fallback: every call fails (non-zero return, message via
@@ -100,9 +102,6 @@ int  mamr_get_counters(mamr_ctx *ctx, mamr_counters *out);
 int  mamr_reset_counters(mamr_ctx *ctx);
 long long mamr_tile_doubles(mamr_ctx *ctx);          /* (nx+2)(ny+2)(nz+2)      */
 long long mamr_pool_bytes(mamr_ctx *ctx);
-/* device pointer of the pool (for zero-copy users, e.g. torch tensors in
- * bench.py) and its strides in doubles */
-void *mamr_pool_device_ptr(mamr_ctx *ctx, long long *var_stride, long long *slot_stride);
 
 /* ---- block data in / out: replaces the fill loops init.c:484-495 --------
  * host layout: tiles[var][i][j][k] with ghosts, (nx+2)(ny+2)(nz+2) doubles

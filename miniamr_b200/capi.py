@@ -57,7 +57,7 @@ class Counters(C.Structure):
 EXPORTS = [
     "mamr_abi_version", "mamr_create", "mamr_destroy", "mamr_last_error", "mamr_sync",
     "mamr_get_counters", "mamr_reset_counters", "mamr_tile_doubles", "mamr_pool_bytes",
-    "mamr_pool_device_ptr", "mamr_upload_block", "mamr_download_block", "mamr_upload_tile",
+    "mamr_upload_block", "mamr_download_block", "mamr_upload_tile",
     "mamr_download_tile", "mamr_zero_block", "mamr_upload_vars", "mamr_download_vars", "mamr_set_topology", "mamr_set_comm_lists",
     "mamr_comm", "mamr_stencil_driver", "mamr_stencil_calc", "mamr_stencil_vars",
     "mamr_check_sum", "mamr_check_sum_vars", "mamr_stage", "mamr_split_block",
@@ -81,7 +81,6 @@ def load_library(path: str = LIB_PATH):
     L.mamr_last_error.restype = C.c_char_p
     L.mamr_tile_doubles.restype = C.c_longlong
     L.mamr_pool_bytes.restype = C.c_longlong
-    L.mamr_pool_device_ptr.restype = C.c_void_p
     L.mamr_create.argtypes = [C.POINTER(Params), C.POINTER(C.c_void_p)]
     for name in EXPORTS:
         fn = getattr(L, name)
@@ -173,11 +172,6 @@ class DeviceMesh:
     def download_vars(self, var_start, num, num_slots, host_ptr):
         self._ck(self.L.mamr_download_vars(self.h, int(var_start), int(num), int(num_slots),
                                            C.c_void_p(int(host_ptr))))
-
-    def pool_ptr(self):
-        vs, ss = C.c_longlong(), C.c_longlong()
-        p = self.L.mamr_pool_device_ptr(self.h, C.byref(vs), C.byref(ss))
-        return p, vs.value, ss.value
 
     def pool_bytes(self):
         return int(self.L.mamr_pool_bytes(self.h))

@@ -95,19 +95,27 @@ bool load_nccl()
       if (r_ != MAMR_OK) return r_;  \
    } while (0)
 
-struct DirLists {
-   std::vector<int> partner, index, num, send_size, recv_size;
-   std::vector<int> block, face_case, send_off, recv_off;
-};
-
 struct EventPair { cudaEvent_t a, b; int cls; };
 
 struct mamr_ctx {
    mamr_params p;
    Geometry g;
    int comm_vars;
-   double *pool = nullptr;
-   size_t pool_bytes = 0;
+   // two pools: the fused stage kernel reads a variable's current pool and
+   // writes the other one; cur[v] says which pool holds variable v
+   double *pool[2] = {nullptr, nullptr};
+   std::vector<unsigned char> cur;
+   size_t pool_bytes = 0;       // of one pool
+   // comm() deferred into the fused kernel: phase-order index (0..5) or -1, and
+   // the first variable of that comm() call (the receive buffers' variable 0)
+   std::vector<signed char> pc_ord;
+   std::vector<int> pc_start;
+   bool fused_geom = false;     // the tile fits the fused kernel
+   bool use_fused = true;       // MAMR_NO_FUSED=1 forces the split path
+   HaloPlan plan[6];
+   bool plan_built[6] = {false, false, false, false, false, false};
+   BoxOp *d_hops[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+   int *d_hbegin[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
    cudaStream_t stream = nullptr;
 
    int num_active = 0;
@@ -157,6 +165,35 @@ struct mamr_ctx {
 namespace {
 
 enum { KC_STENCIL = 0, KC_GHOST = 1, KC_CHECKSUM = 2 };
+
+const int kPerm[6][3] = { {0, 1, 2}, {1, 2, 0}, {2, 0, 1}, {0, 2, 1}, {1, 0, 2}, {2, 1, 0} };
+
+inline int order_index(const mamr_ctx *c, int stage)   // comm.c:51-55
+{
+   return c->p.permute ? ((stage%6) + 6)%6 : 0;
+}
+
+inline double *vpool(mamr_ctx *c, int v) { return c->pool[c->cur[v]]; }
+
+// [v0, v0+n) split into maximal runs that live in the same pool and have the same
+// deferred-comm state
+struct Run { int start, num; };
+std::vector<Run> runs_of(const mamr_ctx *c, int v0, int n, bool split_on_comm)
+{
+   std::vector<Run> r;
+   for (int v = v0; v < v0 + n; v++) {
+      if (!r.empty()) {
+         const int p = r.back().start;
+         if (c->cur[p] == c->cur[v] &&
+             (!split_on_comm || (c->pc_ord[p] == c->pc_ord[v] && c->pc_start[p] == c->pc_start[v]))) {
+            r.back().num++;
+            continue;
+         }
+      }
+      r.push_back({ v, 1 });
+   }
+   return r;
+}
 
 struct KTimer {
    mamr_ctx *c;
@@ -500,20 +537,159 @@ int build_ops(mamr_ctx *c)
    return MAMR_OK;
 }
 
-int flush_pending(mamr_ctx *c)
+// one message per (direction, partner), comm.c:71-84 / 120-151, as NCCL send/recv
+int exchange_dir(mamr_ctx *c, int d)
 {
-   if (c->pend_num > 0) {
-      {
-         KTimer t(c, KC_STENCIL);
-         launch_stencil(c->pool, c->g, c->d_slots, c->num_active, c->pend_start, c->pend_num,
-                        c->p.stencil, c->stream);
+   const DirLists &L = c->cl[d];
+   NC(g_nccl.GroupStart());
+   for (size_t i = 0; i < L.partner.size(); i++) {
+      NC(g_nccl.Recv(c->d_recv[d] + L.recv_off[L.index[i]], (size_t)L.recv_size[i], NCCL_DOUBLE,
+                     L.partner[i], c->nccl, c->stream));
+      NC(g_nccl.Send(c->d_send[d] + L.send_off[L.index[i]], (size_t)L.send_size[i], NCCL_DOUBLE,
+                     L.partner[i], c->nccl, c->stream));
+      c->cnt.counter_halo_recv[d]++;
+      c->cnt.counter_halo_send[d]++;
+      c->cnt.size_mesg_recv[d] += (double)L.recv_size[i]*sizeof(double);
+      c->cnt.size_mesg_send[d] += (double)L.send_size[i]*sizeof(double);
+      c->cnt.counter_face_send[d] += L.num[i];
+      c->cnt.counter_face_recv[d] += L.num[i];
+   }
+   NC(g_nccl.GroupEnd());
+   return MAMR_OK;
+}
+
+// Execute one direction-phased comm() on variables [start, start+num) in place in
+// their current pool (all in the same pool): the split path.
+int comm_split(mamr_ctx *c, int start, int num, int ord)
+{
+   if (c->ops_dirty) CK(build_ops(c));
+   if (c->have_partners && !c->nccl)
+      return fail(MAMR_ENCCL, "comm: off-rank partners present but mamr_nccl_init was not called");
+   double *pool = vpool(c, start);
+   for (int o = 0; o < 3; o++) {
+      const int d = kPerm[ord][o];
+      const DirLists &L = c->cl[d];
+      if (!c->ops_main[d].empty() && num > 0) {
+         KTimer t(c, KC_GHOST);
+         launch_ghost(c->d_ops + c->off_main[d], (int)c->ops_main[d].size(), pool, c->d_send[d],
+                      c->d_recv[d], c->g.var_stride, start, num, c->stream);
+         c->cnt.kernel_launches++;
       }
-      if (c->num_active > 0) c->cnt.kernel_launches++;
-      c->pend_num = 0;
-      CU(cudaGetLastError());
+      if (!L.partner.empty()) {
+         CK(exchange_dir(c, d));
+         if (!c->ops_unpack[d].empty() && num > 0) {
+            KTimer t(c, KC_GHOST);
+            launch_ghost(c->d_ops + c->off_unpack[d], (int)c->ops_unpack[d].size(), pool,
+                         c->d_send[d], c->d_recv[d], c->g.var_stride, start, num, c->stream);
+            c->cnt.kernel_launches++;
+         }
+      }
+   }
+   CU(cudaGetLastError());
+   return MAMR_OK;
+}
+
+// make the deferred comm() of variables [v0, v0+n) real (ghost cells in memory)
+int materialize_comm(mamr_ctx *c, int v0, int n)
+{
+   for (const Run &r : runs_of(c, v0, n, true)) {
+      const int ord = c->pc_ord[r.start];
+      if (ord < 0) continue;
+      if (c->have_partners)
+         return fail(MAMR_EINVAL, "internal: deferred comm with off-rank partners");
+      CK(comm_split(c, r.start, r.num, ord));
+      for (int v = r.start; v < r.start + r.num; v++) c->pc_ord[v] = -1;
    }
    return MAMR_OK;
 }
+
+// build (once per topology and phase order) the halo plan of the fused kernel
+int ensure_plan(mamr_ctx *c, int ord)
+{
+   if (c->plan_built[ord]) return MAMR_OK;
+   PlanInput in;
+   in.g = &c->g;
+   in.stencil = c->p.stencil;
+   in.max_blocks = c->p.max_blocks;
+   in.blocks = &c->blocks;
+   in.cl = c->cl;
+   for (int o = 0; o < 3; o++) in.order[o] = kPerm[ord][o];
+   HaloPlan &P = c->plan[ord];
+   build_halo_plan(in, P);
+   if (P.ok && P.max_ops > 64) {
+      P.ok = false;
+      P.why = "more than 64 halo ops on one block";
+   }
+   c->plan_built[ord] = true;
+   if (!P.ok) return MAMR_OK;
+   CU(cudaStreamSynchronize(c->stream));
+   if (c->d_hops[ord]) CU(cudaFree(c->d_hops[ord]));
+   if (c->d_hbegin[ord]) CU(cudaFree(c->d_hbegin[ord]));
+   c->d_hops[ord] = nullptr;
+   c->d_hbegin[ord] = nullptr;
+   CU(cudaMalloc(&c->d_hops[ord], std::max<size_t>(1, P.ops.size())*sizeof(BoxOp)));
+   CU(cudaMalloc(&c->d_hbegin[ord], P.begin.size()*sizeof(int)));
+   if (!P.ops.empty())
+      CU(cudaMemcpyAsync(c->d_hops[ord], P.ops.data(), P.ops.size()*sizeof(BoxOp),
+                         cudaMemcpyHostToDevice, c->stream));
+   CU(cudaMemcpyAsync(c->d_hbegin[ord], P.begin.data(), P.begin.size()*sizeof(int),
+                      cudaMemcpyHostToDevice, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   return MAMR_OK;
+}
+
+// can a comm() with this phase order be deferred into the fused kernel?
+int fused_ready(mamr_ctx *c, int ord, bool *yes)
+{
+   *yes = false;
+   if (!c->use_fused || !c->fused_geom || c->have_partners || c->num_active == 0)
+      return MAMR_OK;
+   CK(ensure_plan(c, ord));
+   *yes = c->plan[ord].ok;
+   return MAMR_OK;
+}
+
+int flush_pending(mamr_ctx *c)
+{
+   if (c->pend_num == 0) return MAMR_OK;
+   const int v0 = c->pend_start, n = c->pend_num;
+   c->pend_num = 0;
+   for (const Run &r : runs_of(c, v0, n, true)) {
+      const int ord = c->pc_ord[r.start];
+      const int in = c->cur[r.start];
+      if (ord >= 0) {
+         // comm() + stencil in one pass: current pool -> other pool
+         {
+            KTimer t(c, KC_STENCIL);
+            const double *recv[3] = { c->d_recv[0], c->d_recv[1], c->d_recv[2] };
+            launch_fused(c->pool[in], c->pool[in ^ 1], c->g, c->d_slots, c->num_active,
+                         c->d_hops[ord], c->d_hbegin[ord], recv, r.start, r.num,
+                         c->pc_start[r.start], c->p.stencil, c->stream);
+         }
+         if (c->num_active > 0) {
+            c->cnt.kernel_launches++;
+            for (int v = r.start; v < r.start + r.num; v++) c->cur[v] ^= 1;
+         }
+         for (int v = r.start; v < r.start + r.num; v++) c->pc_ord[v] = -1;
+      } else {
+         KTimer t(c, KC_STENCIL);
+         launch_stencil(c->pool[in], c->g, c->d_slots, c->num_active, r.start, r.num,
+                        c->p.stencil, c->stream);
+         if (c->num_active > 0) c->cnt.kernel_launches++;
+      }
+   }
+   CU(cudaGetLastError());
+   return MAMR_OK;
+}
+
+// everything queued for [v0, v0+n) becomes visible in memory (ghost cells too)
+int settle(mamr_ctx *c, int v0, int n)
+{
+   CK(flush_pending(c));
+   return materialize_comm(c, v0, n);
+}
+
+int settle_all(mamr_ctx *c) { return settle(c, 0, c->p.num_vars); }
 
 int check_slot(mamr_ctx *c, int slot)
 {
@@ -571,11 +747,17 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
    memset(&c->cnt, 0, sizeof c->cnt);
    c->cs_valid.assign(p.num_vars, 0);
    c->cs_cache.assign(p.num_vars, 0.0);
-   std::string err;
-   if (!stencil_configure(g, err)) {
+   c->cur.assign(p.num_vars, 0);
+   c->pc_ord.assign(p.num_vars, -1);
+   c->pc_start.assign(p.num_vars, 0);
+   std::string err, why;
+   if (!stencil_configure(g, err) || !fused_configure(g, err)) {
       delete c;
       return fail(MAMR_EUNSUPPORTED, "%s", err.c_str());
    }
+   c->fused_geom = fused_supported(g, why);
+   const char *nf = getenv("MAMR_NO_FUSED");
+   c->use_fused = !(nf && nf[0] == '1');
 #define CUC(call)                                                                         \
    do {                                                                                   \
       cudaError_t e_ = (call);                                                            \
@@ -588,8 +770,10 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
    } while (0)
    CUC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
    c->pool_bytes = (size_t)g.var_stride*p.num_vars*sizeof(double);
-   CUC(cudaMalloc(&c->pool, c->pool_bytes));
-   CUC(cudaMemsetAsync(c->pool, 0, c->pool_bytes, c->stream));
+   for (int b = 0; b < 2; b++) {
+      CUC(cudaMalloc(&c->pool[b], c->pool_bytes));
+      CUC(cudaMemsetAsync(c->pool[b], 0, c->pool_bytes, c->stream));
+   }
    CUC(cudaMalloc(&c->d_sums, p.num_vars*sizeof(double)));
    CUC(cudaMallocHost(&c->h_sums, p.num_vars*sizeof(double)));
    CUC(cudaMalloc(&c->d_rops, c->rops_cap*sizeof(RefineOp)));
@@ -610,7 +794,9 @@ void mamr_destroy(mamr_ctx *c)
    drain_ktimers(c);
    for (cudaEvent_t e : c->ev_free) cudaEventDestroy(e);
    if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
-   cudaFree(c->pool);
+   cudaFree(c->pool[0]);
+   cudaFree(c->pool[1]);
+   for (int o = 0; o < 6; o++) { cudaFree(c->d_hops[o]); cudaFree(c->d_hbegin[o]); }
    cudaFree(c->d_slots);
    cudaFree(c->d_ops);
    for (int d = 0; d < 3; d++) { cudaFree(c->d_send[d]); cudaFree(c->d_recv[d]); }
@@ -629,7 +815,7 @@ void mamr_destroy(mamr_ctx *c)
 int mamr_sync(mamr_ctx *c)
 {
    if (!c) return fail(MAMR_EINVAL, "null context");
-   CK(flush_pending(c));
+   CK(settle_all(c));
    CU(cudaStreamSynchronize(c->stream));
    return MAMR_OK;
 }
@@ -649,26 +835,20 @@ int mamr_reset_counters(mamr_ctx *c)
 }
 
 long long mamr_tile_doubles(mamr_ctx *c) { return c ? c->g.tile : 0; }
-long long mamr_pool_bytes(mamr_ctx *c) { return c ? (long long)c->pool_bytes : 0; }
-
-void *mamr_pool_device_ptr(mamr_ctx *c, long long *var_stride, long long *slot_stride)
-{
-   if (!c) return nullptr;
-   if (var_stride) *var_stride = c->g.var_stride;
-   if (slot_stride) *slot_stride = c->g.tile_stride;
-   return c->pool;
-}
+long long mamr_pool_bytes(mamr_ctx *c) { return c ? 2*(long long)c->pool_bytes : 0; }
 
 // ---- block data in / out ---------------------------------------------------
 int mamr_upload_block(mamr_ctx *c, int slot, const double *tiles)
 {
    CK(check_slot(c, slot));
    if (!tiles) return fail(MAMR_EINVAL, "null tiles");
-   CK(flush_pending(c));
+   CK(settle_all(c));
    const Geometry &g = c->g;
-   CU(cudaMemcpy2DAsync(c->pool + tile_base(g, slot), g.var_stride*sizeof(double), tiles,
-                        g.tile*sizeof(double), g.tile*sizeof(double), c->p.num_vars,
-                        cudaMemcpyHostToDevice, c->stream));
+   for (const Run &r : runs_of(c, 0, c->p.num_vars, false))
+      CU(cudaMemcpy2DAsync(vpool(c, r.start) + (long long)r.start*g.var_stride + tile_base(g, slot),
+                           g.var_stride*sizeof(double), tiles + (size_t)r.start*g.tile,
+                           g.tile*sizeof(double), g.tile*sizeof(double), r.num,
+                           cudaMemcpyHostToDevice, c->stream));
    CU(cudaStreamSynchronize(c->stream));
    touch_all(c);
    return MAMR_OK;
@@ -678,11 +858,13 @@ int mamr_download_block(mamr_ctx *c, int slot, double *tiles)
 {
    CK(check_slot(c, slot));
    if (!tiles) return fail(MAMR_EINVAL, "null tiles");
-   CK(flush_pending(c));
+   CK(settle_all(c));
    const Geometry &g = c->g;
-   CU(cudaMemcpy2DAsync(tiles, g.tile*sizeof(double), c->pool + tile_base(g, slot),
-                        g.var_stride*sizeof(double), g.tile*sizeof(double), c->p.num_vars,
-                        cudaMemcpyDeviceToHost, c->stream));
+   for (const Run &r : runs_of(c, 0, c->p.num_vars, false))
+      CU(cudaMemcpy2DAsync(tiles + (size_t)r.start*g.tile, g.tile*sizeof(double),
+                           vpool(c, r.start) + (long long)r.start*g.var_stride + tile_base(g, slot),
+                           g.var_stride*sizeof(double), g.tile*sizeof(double), r.num,
+                           cudaMemcpyDeviceToHost, c->stream));
    CU(cudaStreamSynchronize(c->stream));
    return MAMR_OK;
 }
@@ -691,9 +873,9 @@ int mamr_upload_tile(mamr_ctx *c, int slot, int var, const double *tile)
 {
    CK(check_slot(c, slot));
    if (var < 0 || var >= c->p.num_vars || !tile) return fail(MAMR_EINVAL, "bad var %d", var);
-   CK(flush_pending(c));
+   CK(settle(c, var, 1));
    const Geometry &g = c->g;
-   CU(cudaMemcpyAsync(c->pool + (long long)var*g.var_stride + tile_base(g, slot), tile,
+   CU(cudaMemcpyAsync(vpool(c, var) + (long long)var*g.var_stride + tile_base(g, slot), tile,
                       g.tile*sizeof(double), cudaMemcpyHostToDevice, c->stream));
    CU(cudaStreamSynchronize(c->stream));
    c->cs_valid[var] = 0;
@@ -705,9 +887,9 @@ int mamr_download_tile(mamr_ctx *c, int slot, int var, double *tile)
 {
    CK(check_slot(c, slot));
    if (var < 0 || var >= c->p.num_vars || !tile) return fail(MAMR_EINVAL, "bad var %d", var);
-   CK(flush_pending(c));
+   CK(settle(c, var, 1));
    const Geometry &g = c->g;
-   CU(cudaMemcpyAsync(tile, c->pool + (long long)var*g.var_stride + tile_base(g, slot),
+   CU(cudaMemcpyAsync(tile, vpool(c, var) + (long long)var*g.var_stride + tile_base(g, slot),
                       g.tile*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
    CU(cudaStreamSynchronize(c->stream));
    return MAMR_OK;
@@ -716,10 +898,11 @@ int mamr_download_tile(mamr_ctx *c, int slot, int var, double *tile)
 int mamr_zero_block(mamr_ctx *c, int slot)
 {
    CK(check_slot(c, slot));
-   CK(flush_pending(c));
+   CK(settle_all(c));
    const Geometry &g = c->g;
-   CU(cudaMemset2DAsync(c->pool + tile_base(g, slot), g.var_stride*sizeof(double), 0,
-                        g.tile*sizeof(double), c->p.num_vars, c->stream));
+   for (const Run &r : runs_of(c, 0, c->p.num_vars, false))
+      CU(cudaMemset2DAsync(vpool(c, r.start) + (long long)r.start*g.var_stride + tile_base(g, slot),
+                           g.var_stride*sizeof(double), 0, g.tile*sizeof(double), r.num, c->stream));
    touch_all(c);
    return MAMR_OK;
 }
@@ -731,10 +914,10 @@ int mamr_upload_vars(mamr_ctx *c, int var_start, int num, int num_slots, const d
        num_slots > c->p.max_blocks)
       return fail(MAMR_EINVAL, "upload_vars: bad range vars [%d,%d) slots %d", var_start,
                   var_start + num, num_slots);
-   CK(flush_pending(c));
+   CK(settle(c, var_start, num));
    const Geometry &g = c->g;
    for (int v = 0; v < num; v++)
-      CU(cudaMemcpy2DAsync(c->pool + (long long)(var_start + v)*g.var_stride,
+      CU(cudaMemcpy2DAsync(vpool(c, var_start + v) + (long long)(var_start + v)*g.var_stride,
                            g.tile_stride*sizeof(double),
                            host + (size_t)v*num_slots*g.tile, g.tile*sizeof(double),
                            g.tile*sizeof(double), num_slots, cudaMemcpyHostToDevice, c->stream));
@@ -749,11 +932,11 @@ int mamr_download_vars(mamr_ctx *c, int var_start, int num, int num_slots, doubl
        num_slots > c->p.max_blocks)
       return fail(MAMR_EINVAL, "download_vars: bad range vars [%d,%d) slots %d", var_start,
                   var_start + num, num_slots);
-   CK(flush_pending(c));
+   CK(settle(c, var_start, num));
    const Geometry &g = c->g;
    for (int v = 0; v < num; v++)
       CU(cudaMemcpy2DAsync(host + (size_t)v*num_slots*g.tile, g.tile*sizeof(double),
-                           c->pool + (long long)(var_start + v)*g.var_stride,
+                           vpool(c, var_start + v) + (long long)(var_start + v)*g.var_stride,
                            g.tile_stride*sizeof(double), g.tile*sizeof(double), num_slots,
                            cudaMemcpyDeviceToHost, c->stream));
    CU(cudaStreamSynchronize(c->stream));
@@ -767,7 +950,7 @@ int mamr_set_topology(mamr_ctx *c, int num_active, const mamr_block *sorted_bloc
       return fail(MAMR_EINVAL, "bad topology arguments");
    if (num_active > c->p.max_blocks)
       return fail(MAMR_EINVAL, "num_active %d > max_blocks %d", num_active, c->p.max_blocks);
-   CK(flush_pending(c));
+   CK(settle_all(c));
    for (int a = 0; a < num_active; a++)
       if (sorted_blocks[a].slot < 0 || sorted_blocks[a].slot >= c->p.max_blocks)
          return fail(MAMR_EINVAL, "active block %d has slot %d out of range", a, sorted_blocks[a].slot);
@@ -793,6 +976,7 @@ int mamr_set_topology(mamr_ctx *c, int num_active, const mamr_block *sorted_bloc
                          cudaMemcpyHostToDevice, c->stream));
    CU(cudaStreamSynchronize(c->stream));
    c->ops_dirty = true;
+   for (int o = 0; o < 6; o++) c->plan_built[o] = false;
    touch_all(c);
    return MAMR_OK;
 }
@@ -800,7 +984,8 @@ int mamr_set_topology(mamr_ctx *c, int num_active, const mamr_block *sorted_bloc
 int mamr_set_comm_lists(mamr_ctx *c, const mamr_comm_dir dirs[3])
 {
    if (!c || !dirs) return fail(MAMR_EINVAL, "null argument");
-   CK(flush_pending(c));
+   CK(settle_all(c));
+   for (int o = 0; o < 6; o++) c->plan_built[o] = false;
    for (int d = 0; d < 3; d++) {
       const mamr_comm_dir &s = dirs[d];
       DirLists &L = c->cl[d];
@@ -825,6 +1010,9 @@ int mamr_set_comm_lists(mamr_ctx *c, const mamr_comm_dir dirs[3])
             return fail(MAMR_EINVAL, "dir %d face %d slot out of range", d, f);
    }
    c->ops_dirty = true;
+   c->have_partners = false;
+   for (int d = 0; d < 3; d++)
+      if (!c->cl[d].partner.empty()) c->have_partners = true;
    return MAMR_OK;
 }
 
@@ -834,49 +1022,26 @@ int mamr_comm(mamr_ctx *c, int start, int num_comm, int stage)
    if (!c) return fail(MAMR_EINVAL, "null context");
    if (start < 0 || num_comm < 0 || start + num_comm > c->p.num_vars)
       return fail(MAMR_EINVAL, "comm: bad variable range [%d,%d)", start, start + num_comm);
-   CK(flush_pending(c));
-   if (c->ops_dirty) CK(build_ops(c));
-   if (c->have_partners && !c->nccl)
-      return fail(MAMR_ENCCL, "comm: off-rank partners present but mamr_nccl_init was not called");
-   static const int perm[6][3] = { {0, 1, 2}, {1, 2, 0}, {2, 0, 1}, {0, 2, 1}, {1, 0, 2}, {2, 1, 0} };
-   for (int o = 0; o < 3; o++) {
-      const int d = c->p.permute ? perm[((stage%6) + 6)%6][o] : o;   // comm.c:51-55
-      const DirLists &L = c->cl[d];
-      if (!c->ops_main[d].empty() && num_comm > 0) {
-         KTimer t(c, KC_GHOST);
-         launch_ghost(c->d_ops + c->off_main[d], (int)c->ops_main[d].size(), c->pool,
-                      c->d_send[d], c->d_recv[d], c->g.var_stride, start, num_comm, c->stream);
-         c->cnt.kernel_launches++;
+   // a queued stencil or an earlier deferred comm() of these variables comes first
+   CK(settle(c, start, num_comm));
+   if (c->ops_dirty) CK(build_ops(c));   // also validates the topology (comm.c:198-201)
+   const int ord = order_index(c, stage);
+   bool defer = false;
+   CK(fused_ready(c, ord, &defer));
+   if (defer) {
+      // the fused kernel performs this exchange when the stencil of the variables
+      // is launched; anything else that needs the ghost cells materialises it
+      for (int v = start; v < start + num_comm; v++) {
+         c->pc_ord[v] = (signed char)ord;
+         c->pc_start[v] = start;
       }
-      if (!L.partner.empty()) {
-         // one message per (direction, partner), comm.c:71-84 / 120-151
-         NC(g_nccl.GroupStart());
-         for (size_t i = 0; i < L.partner.size(); i++) {
-            NC(g_nccl.Recv(c->d_recv[d] + L.recv_off[L.index[i]], (size_t)L.recv_size[i],
-                           NCCL_DOUBLE, L.partner[i], c->nccl, c->stream));
-            NC(g_nccl.Send(c->d_send[d] + L.send_off[L.index[i]], (size_t)L.send_size[i],
-                           NCCL_DOUBLE, L.partner[i], c->nccl, c->stream));
-            c->cnt.counter_halo_recv[d]++;
-            c->cnt.counter_halo_send[d]++;
-            c->cnt.size_mesg_recv[d] += (double)L.recv_size[i]*sizeof(double);
-            c->cnt.size_mesg_send[d] += (double)L.send_size[i]*sizeof(double);
-            c->cnt.counter_face_send[d] += L.num[i];
-            c->cnt.counter_face_recv[d] += L.num[i];
-         }
-         NC(g_nccl.GroupEnd());
-         if (!c->ops_unpack[d].empty() && num_comm > 0) {
-            KTimer t(c, KC_GHOST);
-            launch_ghost(c->d_ops + c->off_unpack[d], (int)c->ops_unpack[d].size(), c->pool,
-                         c->d_send[d], c->d_recv[d], c->g.var_stride, start, num_comm,
-                         c->stream);
-            c->cnt.kernel_launches++;
-         }
-      }
+   } else
+      for (const Run &r : runs_of(c, start, num_comm, false)) CK(comm_split(c, r.start, r.num, ord));
+   for (int d = 0; d < 3; d++) {
       c->cnt.counter_same[d] += c->n_same[d];
       c->cnt.counter_diff[d] += c->n_diff[d];
       c->cnt.counter_bc[d] += c->n_bc[d];
    }
-   CU(cudaGetLastError());
    return MAMR_OK;
 }
 
@@ -918,12 +1083,12 @@ int mamr_check_sum_vars(mamr_ctx *c, int var_start, int num, double *sums)
    if (var_start < 0 || num <= 0 || var_start + num > c->p.num_vars)
       return fail(MAMR_EINVAL, "check_sum: bad variable range [%d,%d)", var_start, var_start + num);
    CK(flush_pending(c));
-   {
+   for (const Run &r : runs_of(c, var_start, num, false)) {
       KTimer t(c, KC_CHECKSUM);
-      launch_checksum(c->pool, c->g, c->d_slots, c->num_active, var_start, num, c->d_partials,
-                      c->d_sums, c->stream);
+      launch_checksum(vpool(c, r.start), c->g, c->d_slots, c->num_active, r.start, r.num,
+                      c->d_partials, c->d_sums + (r.start - var_start), c->stream);
+      c->cnt.kernel_launches += c->num_active > 0 ? 2 : 1;
    }
-   c->cnt.kernel_launches += c->num_active > 0 ? 2 : 1;
    CU(cudaGetLastError());
    if (c->p.num_ranks > 1) {
       if (!c->nccl) return fail(MAMR_ENCCL, "check_sum: mamr_nccl_init was not called");
@@ -995,11 +1160,13 @@ int mamr_split_block(mamr_ctx *c, int parent_slot, const int child_slots[8])
       if (child_slots[o] == parent_slot) return fail(MAMR_EINVAL, "split: child slot equals parent");
       op.child[o] = child_slots[o];
    }
-   CK(flush_pending(c));
+   CK(settle_all(c));
    RefineOp *d;
    CK(push_rop(c, op, &d));
-   launch_split(c->pool, c->g, d, 1, c->p.num_vars, c->stream);
-   c->cnt.kernel_launches++;
+   for (const Run &r : runs_of(c, 0, c->p.num_vars, false)) {
+      launch_split(vpool(c, r.start), c->g, d, 1, r.start, r.num, c->stream);
+      c->cnt.kernel_launches++;
+   }
    CU(cudaGetLastError());
    touch_all(c);
    return MAMR_OK;
@@ -1015,11 +1182,13 @@ int mamr_consolidate_block(mamr_ctx *c, const int child_slots[8], int parent_slo
       if (child_slots[o] == parent_slot) return fail(MAMR_EINVAL, "consolidate: child slot equals parent");
       op.child[o] = child_slots[o];
    }
-   CK(flush_pending(c));
+   CK(settle_all(c));
    RefineOp *d;
    CK(push_rop(c, op, &d));
-   launch_consolidate(c->pool, c->g, d, 1, c->p.num_vars, c->stream);
-   c->cnt.kernel_launches++;
+   for (const Run &r : runs_of(c, 0, c->p.num_vars, false)) {
+      launch_consolidate(vpool(c, r.start), c->g, d, 1, r.start, r.num, c->stream);
+      c->cnt.kernel_launches++;
+   }
    CU(cudaGetLastError());
    touch_all(c);
    return MAMR_OK;
@@ -1031,8 +1200,10 @@ int mamr_pack_block(mamr_ctx *c, int slot, double *payload)
    if (!payload) return fail(MAMR_EINVAL, "null payload");
    CK(flush_pending(c));
    const size_t n = (size_t)c->p.num_vars*c->p.nx*c->p.ny*c->p.nz;
-   launch_pack_block(c->pool, c->g, slot, c->p.num_vars, c->d_payload, c->stream);
-   c->cnt.kernel_launches++;
+   for (const Run &r : runs_of(c, 0, c->p.num_vars, false)) {
+      launch_pack_block(vpool(c, r.start), c->g, slot, r.start, r.num, c->d_payload, c->stream);
+      c->cnt.kernel_launches++;
+   }
    CU(cudaMemcpyAsync(payload, c->d_payload, n*sizeof(double), cudaMemcpyDeviceToHost, c->stream));
    CU(cudaStreamSynchronize(c->stream));
    c->cnt.migrate_bytes += (double)n*sizeof(double);
@@ -1043,11 +1214,13 @@ int mamr_unpack_block(mamr_ctx *c, int slot, const double *payload)
 {
    CK(check_slot(c, slot));
    if (!payload) return fail(MAMR_EINVAL, "null payload");
-   CK(flush_pending(c));
+   CK(settle_all(c));
    const size_t n = (size_t)c->p.num_vars*c->p.nx*c->p.ny*c->p.nz;
    CU(cudaMemcpyAsync(c->d_payload, payload, n*sizeof(double), cudaMemcpyHostToDevice, c->stream));
-   launch_unpack_block(c->pool, c->g, slot, c->p.num_vars, c->d_payload, c->stream);
-   c->cnt.kernel_launches++;
+   for (const Run &r : runs_of(c, 0, c->p.num_vars, false)) {
+      launch_unpack_block(vpool(c, r.start), c->g, slot, r.start, r.num, c->d_payload, c->stream);
+      c->cnt.kernel_launches++;
+   }
    CU(cudaStreamSynchronize(c->stream));
    touch_all(c);
    return MAMR_OK;
@@ -1061,8 +1234,10 @@ int mamr_send_block(mamr_ctx *c, int slot, int dest_rank)
       return fail(MAMR_EINVAL, "send_block: bad destination rank %d", dest_rank);
    CK(flush_pending(c));
    const size_t n = (size_t)c->p.num_vars*c->p.nx*c->p.ny*c->p.nz;
-   launch_pack_block(c->pool, c->g, slot, c->p.num_vars, c->d_payload, c->stream);
-   c->cnt.kernel_launches++;
+   for (const Run &r : runs_of(c, 0, c->p.num_vars, false)) {
+      launch_pack_block(vpool(c, r.start), c->g, slot, r.start, r.num, c->d_payload, c->stream);
+      c->cnt.kernel_launches++;
+   }
    NC(g_nccl.Send(c->d_payload, n, NCCL_DOUBLE, dest_rank, c->nccl, c->stream));
    c->cnt.migrate_bytes += (double)n*sizeof(double);
    CU(cudaGetLastError());
@@ -1075,11 +1250,13 @@ int mamr_recv_block(mamr_ctx *c, int slot, int src_rank)
    if (!c->nccl) return fail(MAMR_ENCCL, "recv_block: mamr_nccl_init was not called");
    if (src_rank < 0 || src_rank >= c->p.num_ranks || src_rank == c->p.rank)
       return fail(MAMR_EINVAL, "recv_block: bad source rank %d", src_rank);
-   CK(flush_pending(c));
+   CK(settle_all(c));
    const size_t n = (size_t)c->p.num_vars*c->p.nx*c->p.ny*c->p.nz;
    NC(g_nccl.Recv(c->d_payload, n, NCCL_DOUBLE, src_rank, c->nccl, c->stream));
-   launch_unpack_block(c->pool, c->g, slot, c->p.num_vars, c->d_payload, c->stream);
-   c->cnt.kernel_launches++;
+   for (const Run &r : runs_of(c, 0, c->p.num_vars, false)) {
+      launch_unpack_block(vpool(c, r.start), c->g, slot, r.start, r.num, c->d_payload, c->stream);
+      c->cnt.kernel_launches++;
+   }
    CU(cudaGetLastError());
    touch_all(c);
    return MAMR_OK;

@@ -37,12 +37,6 @@ struct FaceOp {
    int mem;                       // FaceMem bits
 };
 
-// split / consolidate work item: parent slot + 8 child slots
-struct RefineOp {
-   int parent;
-   int child[8];
-};
-
 struct Geometry {
    int n[3];               // nx, ny, nz
    int str[3];             // element strides of i, j, k inside a tile
@@ -50,6 +44,68 @@ struct Geometry {
    long long tile_stride;  // tile padded to a multiple of 16 doubles (128 B)
    long long var_stride;   // max_blocks * tile_stride
 };
+
+// ---------------------------------------------------------------------------
+// Halo-gather op of the fused stage kernel (fused.cu) and of the pack kernel of
+// the multi-GPU path: "fill a 3-D box of cells from a source through one of the
+// FaceMode transforms".  plan.cu resolves, for every ghost region of every
+// active block, where its value comes from after the three direction phases of
+// comm() (a chain of same-level / boundary hops ends in an interior cell, a
+// stored ghost cell or a receive buffer) and emits one BoxOp per region.
+// ---------------------------------------------------------------------------
+enum BoxMem : int { BM_POOL = 0, BM_BUF0 = 1 /* +dir: send (dst) or recv (src) buffer */ };
+
+struct BoxOp {
+   long long dst_base;   // element offset of the box origin: inside the tile (fused kernel)
+                         // or inside the send buffer (pack kernel), variable `start`
+   long long src_base;   // element offset in the pool (slot*tile_stride + cell) or recv buffer
+   long long dst_vs, src_vs;   // element stride between consecutive variables (buffers only;
+                               // the pool always uses Geometry::var_stride)
+   int ext[3];           // box extents along i, j, k
+   int dst_str[3];       // element strides of i, j, k on the destination side
+   int src_str[3];       // ... and on the source side
+   int S, F;             // FM_SUM4: source strides of the slow / fast in-face axis
+   int first;            // index of the op's first cell in the block's flattened halo list
+   short mode;           // FaceMode
+   unsigned char dst_mem, src_mem;   // BoxMem
+};
+
+// host copy of one direction of the reference's comm lists (comm.h:38-55)
+struct DirLists {
+   std::vector<int> partner, index, num, send_size, recv_size;
+   std::vector<int> block, face_case, send_off, recv_off;
+};
+
+// what plan.cu reads: the topology as the reference's globals describe it
+struct PlanInput {
+   const Geometry *g;
+   int stencil;
+   int max_blocks;
+   const std::vector<mamr_block> *blocks;   // sorted_list order
+   const DirLists *cl;                      // [3]
+   int order[3];                            // direction of phase 0, 1, 2 (comm.c:51-55)
+};
+
+// per launch: CSR of ops by active block
+struct HaloPlan {
+   std::vector<BoxOp> ops;
+   std::vector<int> begin;   // num_active + 1
+   int max_ops = 0;          // largest op count of one block
+   bool ok = false;          // every ghost region resolved without an unsupported chain
+   std::string why;          // reason when !ok
+};
+
+// resolve every ghost region of every active block (fused kernel input)
+void build_halo_plan(const PlanInput &in, HaloPlan &out);
+// ops that fill the send buffer of direction phase `phase` from resolved sources
+bool build_pack_plan(const PlanInput &in, int phase, std::vector<BoxOp> &ops, std::string &why);
+
+// split / consolidate work item: parent slot + 8 child slots
+struct RefineOp {
+   int parent;
+   int child[8];
+};
+
 
 // kernels (launchers) -------------------------------------------------------
 void launch_ghost(const FaceOp *d_ops, int n_ops, double *pool, double *send_buf,
@@ -62,13 +118,24 @@ void launch_checksum(const double *pool, const Geometry &g, const int *d_slots,
                      int num_active, int var_start, int num_vars, double *d_partials,
                      double *d_sums, cudaStream_t s);
 void launch_split(double *pool, const Geometry &g, const RefineOp *d_ops, int n_ops,
-                  int num_vars, cudaStream_t s);
+                  int var_start, int num_vars, cudaStream_t s);
 void launch_consolidate(double *pool, const Geometry &g, const RefineOp *d_ops,
-                        int n_ops, int num_vars, cudaStream_t s);
-void launch_pack_block(const double *pool, const Geometry &g, int slot, int num_vars,
-                       double *d_payload, cudaStream_t s);
-void launch_unpack_block(double *pool, const Geometry &g, int slot, int num_vars,
-                         const double *d_payload, cudaStream_t s);
+                        int n_ops, int var_start, int num_vars, cudaStream_t s);
+void launch_pack_block(const double *pool, const Geometry &g, int slot, int var_start,
+                       int num_vars, double *d_payload, cudaStream_t s);
+void launch_unpack_block(double *pool, const Geometry &g, int slot, int var_start,
+                         int num_vars, const double *d_payload, cudaStream_t s);
+// fused halo-gather + stencil: reads pool_in (read-only), writes whole tiles of pool_out
+bool fused_supported(const Geometry &g, std::string &why);
+bool fused_configure(const Geometry &g, std::string &err);
+void launch_fused(const double *pool_in, double *pool_out, const Geometry &g,
+                  const int *d_slots, int num_active, const BoxOp *d_ops, const int *d_begin,
+                  const double *const recv[3], int var_start, int num_vars, int buf_var0,
+                  int stencil, cudaStream_t s);
+// generic executor of BoxOps whose destination is a send buffer or the pool
+void launch_boxops(const BoxOp *d_ops, int n_ops, const double *pool_in, double *pool_out,
+                   long long var_stride, double *const send[3], const double *const recv[3],
+                   int var_start, int num_vars, int buf_var0, cudaStream_t s);
 int stencil_smem_bytes(const Geometry &g);
 bool stencil_configure(const Geometry &g, std::string &err);
 

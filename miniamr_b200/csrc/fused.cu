@@ -1,0 +1,374 @@
+// Fused stage kernel: comm() + stencil_calc() of one variable group in ONE pass
+// over the block pool (comm.c:42-242 + stencil.c:76-145).
+//
+// The reference exchanges ghost faces in three direction phases and then runs
+// the stencil in place.  On a GPU the exchange phases are the expensive part
+// (the Z phase moves one 8-byte cell per 32-byte sector).  Here every CTA owns
+// one (block, variable) tile and
+//   1. bulk-copies (TMA, cp.async.bulk -> SASS UBLKCP) the i-planes 1..nx of its
+//      tile from the CURRENT pool into shared memory,
+//   2. meanwhile pulls every ghost cell of the tile straight from its origin
+//      (neighbour interior, own interior at a reflective boundary, restriction /
+//      prolongation at a level boundary, a stored ghost cell, a receive buffer)
+//      as resolved by plan.cu — all loads of a thread are issued before the wait
+//      on the bulk copy, so both latencies overlap,
+//   3. writes the gathered ghost cells to shared memory AND to the tile in the
+//      NEXT pool (so stored ghosts are what the reference would hold),
+//   4. marches the (j,k) columns along i exactly like stencil.cu (same summation
+//      order, bit-identical) and writes the new interior to the NEXT pool.
+// The current pool is read-only during the launch, which is what makes the
+// neighbour reads race-free (Jacobi across blocks, as in the reference where all
+// of comm() precedes stencil_calc()); the C ABI flips the variable's current
+// pool afterwards.
+//
+// Roofline: HBM.  Per tile: read n(n+2)^2 doubles (+ halo, mostly L2 hits: the
+// neighbour planes are also some other CTA's own tile), write (n+2)^3 doubles.
+// Algorithmic bytes per cell-variable update: 16 + 8 H/n^3 (the
+// separate ghost-exchange traffic 16 H/n^3 is fused away).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mamr {
+
+namespace {
+
+constexpr int FUSED_THREADS = 256;
+constexpr int MAX_OPS = 64;          // ops per block staged in shared memory
+
+struct FusedArgs {
+   const double *pool_in;
+   double *pool_out;
+   const int *slots;
+   const BoxOp *ops;
+   const int *begin;
+   const double *recv[3];
+   long long tile_stride, var_stride;
+   int num_active, var_start, buf_var0;
+   int nx, ny, nz;
+};
+
+// j-major, k-minor, left to right (stencil.c:111-119)
+__device__ __forceinline__ double plane_sum9(const double *__restrict__ q, int sj)
+{
+   double s = q[-sj - 1] + q[-sj];
+   s += q[-sj + 1];
+   s += q[-1];
+   s += q[0];
+   s += q[1];
+   s += q[sj - 1];
+   s += q[sj];
+   s += q[sj + 1];
+   return s;
+}
+
+// compact copy of a BoxOp in shared memory
+struct SOp {
+   long long src_base, src_vs;
+   int first;                 // flattened index of its first element
+   int dst_base;
+   int e0, e1, e2;            // extents along i, j and k
+   int ds0, ds1, ds2;         // destination strides (tile strides)
+   int ss0, ss1, ss2;
+   int S, F;
+   int mode, src_mem;
+};
+
+template <int STENCIL, int CPT, int Q>
+__global__ void __launch_bounds__(FUSED_THREADS)
+fused_kernel(const FusedArgs A)
+{
+   extern __shared__ __align__(128) unsigned char smem_raw[];
+   const int nx = A.nx, ny = A.ny, nz = A.nz;
+   const int sj = nz + 2;
+   const int plane = (ny + 2)*sj;
+   const int nplanes = nx + 2;
+   double *sm = reinterpret_cast<double *>(smem_raw);
+   SOp *sops = reinterpret_cast<SOp *>(smem_raw + (size_t)nplanes*plane*8);
+   uint64_t *full = reinterpret_cast<uint64_t *>(sops + MAX_OPS);
+
+   const int tid = threadIdx.x;
+   const int a = blockIdx.x%A.num_active;
+   const int vl = blockIdx.x/A.num_active;
+   const int v = A.var_start + vl;
+   const long long tile_off = (long long)v*A.var_stride + (long long)A.slots[a]*A.tile_stride;
+   const double *tin = A.pool_in + tile_off;
+   double *tout = A.pool_out + tile_off;
+
+   const int ob = A.begin[a];
+   const int nops = A.begin[a + 1] - ob;
+   if (tid == 0) {
+      mbar_init(full, 1);
+      fence_barrier_init();
+   }
+   // stage the op table (one thread per op)
+   if (tid < nops) {
+      const BoxOp &g = A.ops[ob + tid];
+      SOp s;
+      s.src_base = g.src_base; s.src_vs = g.src_vs;
+      s.first = g.first; s.dst_base = (int)g.dst_base;
+      s.e0 = g.ext[0]; s.e1 = g.ext[1]; s.e2 = g.ext[2];
+      s.ds0 = g.dst_str[0]; s.ds1 = g.dst_str[1]; s.ds2 = g.dst_str[2];
+      s.ss0 = g.src_str[0]; s.ss1 = g.src_str[1]; s.ss2 = g.src_str[2];
+      s.S = g.S; s.F = g.F;
+      s.mode = g.mode; s.src_mem = g.src_mem;
+      sops[tid] = s;
+   }
+   __syncthreads();
+   if (tid == 0) {
+      const uint32_t bytes = (uint32_t)nx*plane*8u;
+      mbar_arrive_expect_tx(full, bytes);
+      // planes 1..nx are one contiguous run; copy plane by plane (<= 64 KB each)
+      for (int p = 1; p <= nx; p++)
+         bulk_g2s(sm + (size_t)p*plane, tin + (size_t)p*plane, (uint32_t)plane*8u, full);
+   }
+
+   // ---- halo gather: every load is issued before the wait on the bulk copy ----
+   const int last = nops - 1;
+   const int E = nops > 0 ? sops[last].first + sops[last].e0*sops[last].e1*sops[last].e2 : 0;
+   double val[Q];
+   int dsto[Q];
+#pragma unroll
+   for (int q = 0; q < Q; q++) {
+      const int e = tid + q*FUSED_THREADS;
+      dsto[q] = -1;
+      val[q] = 0.0;
+      if (e < E) {
+         int lo = 0, hi = last;
+         while (lo < hi) {                       // last op with first <= e
+            const int mid = (lo + hi + 1) >> 1;
+            if (sops[mid].first <= e) lo = mid; else hi = mid - 1;
+         }
+         const SOp &s = sops[lo];
+         int r = e - s.first;
+         const int c = r%s.e2; r /= s.e2;
+         const int b = r%s.e1;
+         const int aa = r/s.e1;
+         dsto[q] = s.dst_base + aa*s.ds0 + b*s.ds1 + c*s.ds2;
+         const double *base = (s.src_mem == BM_POOL)
+                                 ? A.pool_in + (long long)v*A.var_stride
+                                 : A.recv[s.src_mem - BM_BUF0] + (long long)(v - A.buf_var0)*s.src_vs;
+         base += s.src_base;
+         const int mode = s.mode;
+         if (mode == FM_COPY) {
+            val[q] = __ldg(base + (long long)aa*s.ss0 + b*s.ss1 + c*s.ss2);
+         } else if (mode == FM_PROLONG || mode == FM_REPL) {
+            const double x = __ldg(base + (long long)(aa >> 1)*s.ss0 + (b >> 1)*s.ss1 + (c >> 1)*s.ss2);
+            val[q] = mode == FM_PROLONG ? x/4.0 : x;
+         } else {   // FM_SUM4, left to right, slow index outer (comm.c:1626-1629)
+            const double *p = base + (long long)(2*aa)*s.ss0 + (2*b)*s.ss1 + (2*c)*s.ss2;
+            double t = __ldg(p) + __ldg(p + s.F);
+            t += __ldg(p + s.S);
+            t += __ldg(p + s.S + s.F);
+            val[q] = t;
+         }
+      }
+   }
+
+   // the (j,k) columns this thread owns
+   const int cells = ny*nz;
+   int off[CPT];
+   bool live[CPT];
+#pragma unroll
+   for (int q = 0; q < CPT; q++) {
+      const int c = tid + q*FUSED_THREADS;
+      live[q] = c < cells;
+      const int cc = live[q] ? c : 0;
+      const int j = cc/nz;
+      off[q] = (j + 1)*sj + (cc - j*nz) + 1;
+   }
+
+   mbar_wait(full, 0);
+#pragma unroll
+   for (int q = 0; q < Q; q++)
+      if (dsto[q] >= 0) {
+         sm[dsto[q]] = val[q];
+         tout[dsto[q]] = val[q];
+      }
+   __syncthreads();
+
+   // ---- stencil: march along i, two previous plane contributions in registers --
+   double prev[CPT], cur[CPT];
+#pragma unroll
+   for (int q = 0; q < CPT; q++) {
+      if (STENCIL == 7) {
+         prev[q] = sm[off[q]];
+         cur[q] = sm[plane + off[q]];
+      } else {
+         prev[q] = plane_sum9(sm + off[q], sj);
+         cur[q] = plane_sum9(sm + plane + off[q], sj);
+      }
+   }
+   for (int i = 1; i <= nx; i++) {
+      const double *pc = sm + (size_t)i*plane;
+      const double *pn = pc + plane;
+      double *out = tout + (size_t)i*plane;
+#pragma unroll
+      for (int q = 0; q < CPT; q++) {
+         double r;
+         if (STENCIL == 7) {
+            const double *c = pc + off[q];
+            const double e = pn[off[q]];
+            double s = prev[q] + c[-sj];           // W + S
+            s += c[-1];                            // + D
+            s += cur[q];                           // + C
+            s += c[1];                             // + U
+            s += c[sj];                            // + N
+            s += e;                                // + E
+            r = div_const<7>(s);
+            prev[q] = cur[q];
+            cur[q] = e;
+         } else {
+            const double nxt = plane_sum9(pn + off[q], sj);
+            r = div_const<27>((prev[q] + cur[q]) + nxt);
+            prev[q] = cur[q];
+            cur[q] = nxt;
+         }
+         if (live[q]) out[off[q]] = r;
+      }
+   }
+}
+
+struct FusedPlan {
+   int cpt, q, smem;
+   bool ok;
+};
+
+FusedPlan make_plan(const Geometry &g)
+{
+   FusedPlan p;
+   const int cells = g.n[1]*g.n[2];
+   const int cpt = (cells + FUSED_THREADS - 1)/FUSED_THREADS;
+   p.cpt = 1;
+   while (p.cpt < cpt) p.cpt *= 2;
+   const int halo = g.tile - g.n[0]*g.n[1]*g.n[2];
+   const int q = (halo + FUSED_THREADS - 1)/FUSED_THREADS;
+   p.q = q <= 4 ? 4 : (q <= 8 ? 8 : (q <= 12 ? 12 : 16));
+   p.smem = g.tile*8 + MAX_OPS*(int)sizeof(SOp) + 16;
+   p.ok = p.cpt <= 4 && q <= 16 && p.smem <= 110*1024;
+   return p;
+}
+
+template <int ST, int C, int Q>
+cudaError_t set_attr(int smem)
+{
+   return cudaFuncSetAttribute(fused_kernel<ST, C, Q>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               smem);
+}
+
+#define MAMR_FUSED_VARIANTS(X) \
+   X(1, 4) X(1, 8) X(1, 12) X(1, 16) X(2, 4) X(2, 8) X(2, 12) X(2, 16) X(4, 4) X(4, 8) X(4, 12) X(4, 16)
+
+}  // namespace
+
+bool fused_supported(const Geometry &g, std::string &why)
+{
+   const FusedPlan p = make_plan(g);
+   if (!p.ok) why = "tile does not fit the whole-tile fused kernel (shared memory / column mapping)";
+   return p.ok;
+}
+
+bool fused_configure(const Geometry &g, std::string &err)
+{
+   const FusedPlan p = make_plan(g);
+   if (!p.ok) return true;   // the split path serves this geometry
+   cudaError_t e = cudaSuccess;
+#define X(C, QQ)                                                    \
+   if (e == cudaSuccess && p.cpt == C && p.q == QQ) {               \
+      e = set_attr<7, C, QQ>(p.smem);                               \
+      if (e == cudaSuccess) e = set_attr<27, C, QQ>(p.smem);        \
+   }
+   MAMR_FUSED_VARIANTS(X)
+#undef X
+   if (e != cudaSuccess) {
+      err = std::string("fused: cudaFuncSetAttribute: ") + cudaGetErrorString(e);
+      return false;
+   }
+   return true;
+}
+
+void launch_fused(const double *pool_in, double *pool_out, const Geometry &g, const int *d_slots,
+                  int num_active, const BoxOp *d_ops, const int *d_begin,
+                  const double *const recv[3], int var_start, int num_vars, int buf_var0,
+                  int stencil, cudaStream_t s)
+{
+   if (num_active <= 0 || num_vars <= 0) return;
+   const FusedPlan p = make_plan(g);
+   FusedArgs A;
+   A.pool_in = pool_in; A.pool_out = pool_out; A.slots = d_slots;
+   A.ops = d_ops; A.begin = d_begin;
+   for (int d = 0; d < 3; d++) A.recv[d] = recv ? recv[d] : nullptr;
+   A.tile_stride = g.tile_stride; A.var_stride = g.var_stride;
+   A.num_active = num_active; A.buf_var0 = buf_var0;
+   A.nx = g.n[0]; A.ny = g.n[1]; A.nz = g.n[2];
+   const int max_vars = (int)(((1LL << 31) - 1)/num_active);
+   for (int v0 = 0; v0 < num_vars; v0 += max_vars) {
+      const int nv = (num_vars - v0 < max_vars) ? num_vars - v0 : max_vars;
+      const unsigned grid = (unsigned)((long long)num_active*nv);
+      A.var_start = var_start + v0;
+#define X(C, QQ)                                                                       \
+   if (p.cpt == C && p.q == QQ) {                                                      \
+      if (stencil == 7) fused_kernel<7, C, QQ><<<grid, FUSED_THREADS, p.smem, s>>>(A); \
+      else fused_kernel<27, C, QQ><<<grid, FUSED_THREADS, p.smem, s>>>(A);             \
+   }
+      MAMR_FUSED_VARIANTS(X)
+#undef X
+   }
+}
+
+// ---------------------------------------------------------------------------
+// Generic BoxOp executor: grid = (ops, variables).  Used to pack the send
+// buffers of the multi-GPU path from resolved origins (pack_face, comm.c:254-401).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+boxop_kernel(const BoxOp *__restrict__ ops, const double *__restrict__ pool_in,
+             double *__restrict__ pool_out, long long var_stride, double *send0, double *send1,
+             double *send2, const double *recv0, const double *recv1, const double *recv2,
+             int var_start, int buf_var0)
+{
+   const BoxOp op = ops[blockIdx.x];
+   const int v = var_start + blockIdx.y;
+   double *sends[3] = { send0, send1, send2 };
+   const double *recvs[3] = { recv0, recv1, recv2 };
+   double *dst = (op.dst_mem == BM_POOL)
+                    ? pool_out + (long long)v*var_stride
+                    : sends[op.dst_mem - BM_BUF0] + (long long)(v - buf_var0)*op.dst_vs;
+   const double *src = (op.src_mem == BM_POOL)
+                          ? pool_in + (long long)v*var_stride
+                          : recvs[op.src_mem - BM_BUF0] + (long long)(v - buf_var0)*op.src_vs;
+   dst += op.dst_base;
+   src += op.src_base;
+   const int n = op.ext[0]*op.ext[1]*op.ext[2];
+   for (int e = threadIdx.x; e < n; e += blockDim.x) {
+      int r = e;
+      const int c = r%op.ext[2]; r /= op.ext[2];
+      const int b = r%op.ext[1];
+      const int a = r/op.ext[1];
+      double x;
+      if (op.mode == FM_COPY || op.mode == FM_DIV4) {
+         x = src[(long long)a*op.src_str[0] + b*op.src_str[1] + c*op.src_str[2]];
+         if (op.mode == FM_DIV4) x = x/4.0;
+      } else if (op.mode == FM_PROLONG || op.mode == FM_REPL) {
+         x = src[(long long)(a >> 1)*op.src_str[0] + (b >> 1)*op.src_str[1] + (c >> 1)*op.src_str[2]];
+         if (op.mode == FM_PROLONG) x = x/4.0;
+      } else {
+         const double *p = src + (long long)(2*a)*op.src_str[0] + (2*b)*op.src_str[1] +
+                           (2*c)*op.src_str[2];
+         x = p[0] + p[op.F];
+         x += p[op.S];
+         x += p[op.S + op.F];
+      }
+      dst[(long long)a*op.dst_str[0] + b*op.dst_str[1] + c*op.dst_str[2]] = x;
+   }
+}
+
+void launch_boxops(const BoxOp *d_ops, int n_ops, const double *pool_in, double *pool_out,
+                   long long var_stride, double *const send[3], const double *const recv[3],
+                   int var_start, int num_vars, int buf_var0, cudaStream_t s)
+{
+   if (n_ops <= 0 || num_vars <= 0) return;
+   dim3 grid((unsigned)n_ops, (unsigned)num_vars);
+   boxop_kernel<<<grid, 128, 0, s>>>(d_ops, pool_in, pool_out, var_stride, send[0], send[1],
+                                     send[2], recv[0], recv[1], recv[2], var_start, buf_var0);
+}
+
+}  // namespace mamr

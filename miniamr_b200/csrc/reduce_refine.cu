@@ -94,14 +94,15 @@ void launch_checksum(const double *pool, const Geometry &g, const int *d_slots,
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 split_kernel(double *__restrict__ pool, const RefineOp *__restrict__ ops, int nx, int ny,
-             int nz, long long tile_stride, long long var_stride)
+             int nz, long long tile_stride, long long var_stride, int var0)
 {
+   const int var = var0 + blockIdx.y;
    const RefineOp op = ops[blockIdx.x >> 3];
    const int o = blockIdx.x & 7;
    const int sj = nz + 2, si = (ny + 2)*sj;
    const int i1 = (o & 1)*(nx/2), j1 = ((o >> 1) & 1)*(ny/2), k1 = (o >> 2)*(nz/2);
-   const double *par = pool + (long long)blockIdx.y*var_stride + (long long)op.parent*tile_stride;
-   double *ch = pool + (long long)blockIdx.y*var_stride + (long long)op.child[o]*tile_stride;
+   const double *par = pool + (long long)var*var_stride + (long long)op.parent*tile_stride;
+   double *ch = pool + (long long)var*var_stride + (long long)op.child[o]*tile_stride;
    const int cells = nx*ny*nz;
    for (int c = threadIdx.x; c < cells; c += blockDim.x) {
       const int i = c/(ny*nz), r = c - i*ny*nz, j = r/nz, k = r - j*nz;   // 0-based child cell
@@ -112,12 +113,12 @@ split_kernel(double *__restrict__ pool, const RefineOp *__restrict__ ops, int nx
 }
 
 void launch_split(double *pool, const Geometry &g, const RefineOp *d_ops, int n_ops,
-                  int num_vars, cudaStream_t s)
+                  int var_start, int num_vars, cudaStream_t s)
 {
-   if (n_ops <= 0) return;
+   if (n_ops <= 0 || num_vars <= 0) return;
    dim3 grid((unsigned)n_ops*8u, (unsigned)num_vars);
    split_kernel<<<grid, 256, 0, s>>>(pool, d_ops, g.n[0], g.n[1], g.n[2], g.tile_stride,
-                                     g.var_stride);
+                                     g.var_stride, var_start);
 }
 
 // ---------------------------------------------------------------------------
@@ -127,19 +128,20 @@ void launch_split(double *pool, const Geometry &g, const RefineOp *d_ops, int n_
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 consolidate_kernel(double *__restrict__ pool, const RefineOp *__restrict__ ops, int nx,
-                   int ny, int nz, long long tile_stride, long long var_stride)
+                   int ny, int nz, long long tile_stride, long long var_stride, int var0)
 {
+   const int var = var0 + blockIdx.y;
    const RefineOp op = ops[blockIdx.x];
    const int sj = nz + 2, si = (ny + 2)*sj;
    const int hx = nx/2, hy = ny/2, hz = nz/2;
-   double *par = pool + (long long)blockIdx.y*var_stride + (long long)op.parent*tile_stride;
+   double *par = pool + (long long)var*var_stride + (long long)op.parent*tile_stride;
    const int cells = nx*ny*nz;
    for (int c = threadIdx.x; c < cells; c += blockDim.x) {
       const int i = c/(ny*nz), r = c - i*ny*nz, j = r/nz, k = r - j*nz;   // 0-based parent cell
       const int o = (i >= hx ? 1 : 0) + (j >= hy ? 2 : 0) + (k >= hz ? 4 : 0);
       const int ci = 2*(i - (i >= hx ? hx : 0)) + 1, cj = 2*(j - (j >= hy ? hy : 0)) + 1,
                 ck = 2*(k - (k >= hz ? hz : 0)) + 1;
-      const double *q = pool + (long long)blockIdx.y*var_stride +
+      const double *q = pool + (long long)var*var_stride +
                         (long long)op.child[o]*tile_stride + (size_t)ci*si + cj*sj + ck;
       double s = q[0] + q[si];
       s += q[sj];
@@ -153,12 +155,12 @@ consolidate_kernel(double *__restrict__ pool, const RefineOp *__restrict__ ops, 
 }
 
 void launch_consolidate(double *pool, const Geometry &g, const RefineOp *d_ops, int n_ops,
-                        int num_vars, cudaStream_t s)
+                        int var_start, int num_vars, cudaStream_t s)
 {
-   if (n_ops <= 0) return;
+   if (n_ops <= 0 || num_vars <= 0) return;
    dim3 grid((unsigned)n_ops, (unsigned)num_vars);
    consolidate_kernel<<<grid, 256, 0, s>>>(pool, d_ops, g.n[0], g.n[1], g.n[2],
-                                           g.tile_stride, g.var_stride);
+                                           g.tile_stride, g.var_stride, var_start);
 }
 
 // ---------------------------------------------------------------------------
@@ -167,12 +169,14 @@ void launch_consolidate(double *pool, const Geometry &g, const RefineOp *d_ops, 
 template <bool PACK>
 __global__ void __launch_bounds__(256)
 block_payload_kernel(double *__restrict__ pool, int slot, int nx, int ny, int nz,
-                     long long tile_stride, long long var_stride, double *__restrict__ payload)
+                     long long tile_stride, long long var_stride, double *__restrict__ payload,
+                     int var0)
 {
+   const int var = var0 + blockIdx.y;
    const int sj = nz + 2, si = (ny + 2)*sj;
    const int cells = nx*ny*nz;
-   double *tile = pool + (long long)blockIdx.y*var_stride + (long long)slot*tile_stride;
-   double *pl = payload + (size_t)blockIdx.y*cells;
+   double *tile = pool + (long long)var*var_stride + (long long)slot*tile_stride;
+   double *pl = payload + (size_t)var*cells;
    for (int c = blockIdx.x*blockDim.x + threadIdx.x; c < cells; c += gridDim.x*blockDim.x) {
       const int i = c/(ny*nz), r = c - i*ny*nz, j = r/nz, k = r - j*nz;
       const size_t t = (size_t)(i + 1)*si + (j + 1)*sj + (k + 1);
@@ -181,24 +185,26 @@ block_payload_kernel(double *__restrict__ pool, int slot, int nx, int ny, int nz
    }
 }
 
-void launch_pack_block(const double *pool, const Geometry &g, int slot, int num_vars,
-                       double *d_payload, cudaStream_t s)
+void launch_pack_block(const double *pool, const Geometry &g, int slot, int var_start,
+                       int num_vars, double *d_payload, cudaStream_t s)
 {
+   if (num_vars <= 0) return;
    const int cells = g.n[0]*g.n[1]*g.n[2];
    dim3 grid((unsigned)((cells + 1023)/1024), (unsigned)num_vars);
    block_payload_kernel<true><<<grid, 256, 0, s>>>(const_cast<double *>(pool), slot, g.n[0],
                                                    g.n[1], g.n[2], g.tile_stride,
-                                                   g.var_stride, d_payload);
+                                                   g.var_stride, d_payload, var_start);
 }
 
-void launch_unpack_block(double *pool, const Geometry &g, int slot, int num_vars,
-                         const double *d_payload, cudaStream_t s)
+void launch_unpack_block(double *pool, const Geometry &g, int slot, int var_start,
+                         int num_vars, const double *d_payload, cudaStream_t s)
 {
+   if (num_vars <= 0) return;
    const int cells = g.n[0]*g.n[1]*g.n[2];
    dim3 grid((unsigned)((cells + 1023)/1024), (unsigned)num_vars);
    block_payload_kernel<false><<<grid, 256, 0, s>>>(pool, slot, g.n[0], g.n[1], g.n[2],
                                                     g.tile_stride, g.var_stride,
-                                                    const_cast<double *>(d_payload));
+                                                    const_cast<double *>(d_payload), var_start);
 }
 
 }  // namespace mamr

@@ -25,56 +25,9 @@
 // Roofline: HBM.  Algorithmic bytes per cell-variable update:
 // 16 + 8*H/n^3 (H = ghost cells the stencil needs), SURVEY.md §8(d).
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace mamr {
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p)
-{
-   return (uint32_t)__cvta_generic_to_shared(p);
-}
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
-{
-   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-
-__device__ __forceinline__ void fence_barrier_init()
-{
-   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-                "r"(bytes)
-                : "memory");
-}
-
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-   asm volatile(
-      "{\n"
-      ".reg .pred P1;\n"
-      "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
-      "DONE:\n"
-      "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-
-// 1-D bulk TMA copy global -> shared, completion counted in bytes on `bar`
-__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes,
-                                         uint64_t *bar)
-{
-   asm volatile(
-      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-         "r"(smem_u32(smem_dst)),
-      "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-      : "memory");
-}
 
 // contribution of one staged plane to a (j,k) column
 template <int STENCIL>

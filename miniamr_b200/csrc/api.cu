@@ -121,6 +121,7 @@ struct mamr_ctx {
    int num_active = 0;
    std::vector<mamr_block> blocks;
    int *d_slots = nullptr;
+   int *d_order = nullptr;      // fused kernel: CTA index -> active block index
    size_t slots_cap = 0;
 
    // ghost descriptors, per direction: [local | pack] contiguous, then unpack
@@ -662,7 +663,7 @@ int flush_pending(mamr_ctx *c)
          {
             KTimer t(c, KC_STENCIL);
             const double *recv[3] = { c->d_recv[0], c->d_recv[1], c->d_recv[2] };
-            launch_fused(c->pool[in], c->pool[in ^ 1], c->g, c->d_slots, c->num_active,
+            launch_fused(c->pool[in], c->pool[in ^ 1], c->g, c->d_slots, c->d_order, c->num_active,
                          c->d_hops[ord], c->d_hbegin[ord], recv, r.start, r.num,
                          c->pc_start[r.start], c->p.stencil, c->stream);
          }
@@ -697,6 +698,41 @@ int check_slot(mamr_ctx *c, int slot)
    if (slot < 0 || slot >= c->p.max_blocks)
       return fail(MAMR_EINVAL, "slot %d out of range [0,%d)", slot, c->p.max_blocks);
    return MAMR_OK;
+}
+
+// Order in which the fused kernel visits the blocks.  A Z face is the expensive
+// part of a tile's halo (k is the fastest axis: one 8-byte cell per 32-byte
+// sector), so blocks are visited in +z chains: the tile a CTA pulls its Z halo
+// from is then the tile the neighbouring CTA streams through L2 at about the
+// same time.  Chains start in sorted_list order, which keeps x neighbours close.
+std::vector<int> processing_order(const mamr_ctx *c)
+{
+   const int nb = c->num_active;
+   std::vector<int> slot2idx(c->p.max_blocks, -1), order;
+   std::vector<char> done(nb, 0);
+   for (int a = 0; a < nb; a++) slot2idx[c->blocks[a].slot] = a;
+   auto link = [&](int a, int l) {   // same-level on-rank neighbour through face l, or -1
+      const mamr_block &b = c->blocks[a];
+      if (b.nei_level[l] != b.level) return -1;
+      const int m = b.nei[l][0][0];
+      return (m >= 0 && m < c->p.max_blocks) ? slot2idx[m] : -1;
+   };
+   order.reserve(nb);
+   for (int a0 = 0; a0 < nb; a0++) {
+      if (done[a0]) continue;
+      int a = a0;
+      for (int steps = 0; steps < nb; steps++) {   // walk to the -z end of the chain
+         const int m = link(a, 4);
+         if (m < 0 || done[m]) break;
+         a = m;
+      }
+      while (a >= 0 && !done[a]) {
+         done[a] = 1;
+         order.push_back(a);
+         a = link(a, 5);
+      }
+   }
+   return order;
 }
 
 void touch_all(mamr_ctx *c)
@@ -798,6 +834,7 @@ void mamr_destroy(mamr_ctx *c)
    cudaFree(c->pool[1]);
    for (int o = 0; o < 6; o++) { cudaFree(c->d_hops[o]); cudaFree(c->d_hbegin[o]); }
    cudaFree(c->d_slots);
+   cudaFree(c->d_order);
    cudaFree(c->d_ops);
    for (int d = 0; d < 3; d++) { cudaFree(c->d_send[d]); cudaFree(c->d_recv[d]); }
    cudaFree(c->d_partials);
@@ -959,8 +996,10 @@ int mamr_set_topology(mamr_ctx *c, int num_active, const mamr_block *sorted_bloc
    if ((size_t)num_active > c->slots_cap) {
       CU(cudaStreamSynchronize(c->stream));
       if (c->d_slots) CU(cudaFree(c->d_slots));
+      if (c->d_order) CU(cudaFree(c->d_order));
       c->slots_cap = (size_t)num_active + num_active/4 + 64;
       CU(cudaMalloc(&c->d_slots, c->slots_cap*sizeof(int)));
+      CU(cudaMalloc(&c->d_order, c->slots_cap*sizeof(int)));
    }
    if ((size_t)num_active*c->p.num_vars > c->partials_cap) {
       CU(cudaStreamSynchronize(c->stream));
@@ -971,9 +1010,13 @@ int mamr_set_topology(mamr_ctx *c, int num_active, const mamr_block *sorted_bloc
    std::vector<int> slots(num_active);
    for (int a = 0; a < num_active; a++) slots[a] = sorted_blocks[a].slot;
    CU(cudaStreamSynchronize(c->stream));
-   if (num_active)
+   const std::vector<int> order = processing_order(c);
+   if (num_active) {
       CU(cudaMemcpyAsync(c->d_slots, slots.data(), num_active*sizeof(int),
                          cudaMemcpyHostToDevice, c->stream));
+      CU(cudaMemcpyAsync(c->d_order, order.data(), num_active*sizeof(int),
+                         cudaMemcpyHostToDevice, c->stream));
+   }
    CU(cudaStreamSynchronize(c->stream));
    c->ops_dirty = true;
    for (int o = 0; o < 6; o++) c->plan_built[o] = false;

@@ -129,7 +129,8 @@ void launch_unpack_block(double *pool, const Geometry &g, int slot, int var_star
 bool fused_supported(const Geometry &g, std::string &why);
 bool fused_configure(const Geometry &g, std::string &err);
 void launch_fused(const double *pool_in, double *pool_out, const Geometry &g,
-                  const int *d_slots, int num_active, const BoxOp *d_ops, const int *d_begin,
+                  const int *d_slots, const int *d_order, int num_active, const BoxOp *d_ops,
+                  const int *d_begin,
                   const double *const recv[3], int var_start, int num_vars, int buf_var0,
                   int stencil, cudaStream_t s);
 // generic executor of BoxOps whose destination is a send buffer or the pool

@@ -39,26 +39,55 @@ struct FusedArgs {
    const double *pool_in;
    double *pool_out;
    const int *slots;
+   const int *order;      // processing order: CTA -> active block index
    const BoxOp *ops;
    const int *begin;
    const double *recv[3];
    long long tile_stride, var_stride;
-   int num_active, var_start, buf_var0;
+   int num_active, var_start, var_end, vpc, buf_var0;
    int nx, ny, nz;
+   int chunk;             // 27-point path: i-planes per thread
 };
 
-// j-major, k-minor, left to right (stencil.c:111-119)
-__device__ __forceinline__ double plane_sum9(const double *__restrict__ q, int sj)
+// 27-point path: a thread owns a 2x2 patch of (j,k) columns.  One i-plane of the
+// patch plus its ring is a 4x4 register tile (8 aligned 128-bit shared loads);
+// the four 9-term plane sums are formed from registers in the reference's order.
+struct Patch {
+   double t[4][4];
+};
+
+__device__ __forceinline__ void load_patch(const double *__restrict__ p, int sj, Patch &P)
 {
-   double s = q[-sj - 1] + q[-sj];
-   s += q[-sj + 1];
-   s += q[-1];
-   s += q[0];
-   s += q[1];
-   s += q[sj - 1];
-   s += q[sj];
-   s += q[sj + 1];
+#pragma unroll
+   for (int r = 0; r < 4; r++) {
+      const double2 a = *reinterpret_cast<const double2 *>(p + r*sj);
+      const double2 b = *reinterpret_cast<const double2 *>(p + r*sj + 2);
+      P.t[r][0] = a.x; P.t[r][1] = a.y; P.t[r][2] = b.x; P.t[r][3] = b.y;
+   }
+}
+
+// j-major, k-minor, left to right (stencil.c:111-119)
+__device__ __forceinline__ double patch_sum9(const Patch &P, int jj, int kk)
+{
+   double s = P.t[jj][kk] + P.t[jj][kk + 1];
+   s += P.t[jj][kk + 2];
+   s += P.t[jj + 1][kk];
+   s += P.t[jj + 1][kk + 1];
+   s += P.t[jj + 1][kk + 2];
+   s += P.t[jj + 2][kk];
+   s += P.t[jj + 2][kk + 1];
+   s += P.t[jj + 2][kk + 2];
    return s;
+}
+
+__device__ __forceinline__ void patch_sums(const double *__restrict__ p, int sj, double out[4])
+{
+   Patch P;
+   load_patch(p, sj, P);
+   out[0] = patch_sum9(P, 0, 0);
+   out[1] = patch_sum9(P, 0, 1);
+   out[2] = patch_sum9(P, 1, 0);
+   out[3] = patch_sum9(P, 1, 1);
 }
 
 // compact copy of a BoxOp in shared memory
@@ -73,8 +102,9 @@ struct SOp {
    int mode, src_mem;
 };
 
+// mbarrier wait with a C++-visible parity (phase) argument
 template <int STENCIL, int CPT, int Q>
-__global__ void __launch_bounds__(FUSED_THREADS)
+__global__ void __launch_bounds__(FUSED_THREADS, 2)
 fused_kernel(const FusedArgs A)
 {
    extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -82,22 +112,25 @@ fused_kernel(const FusedArgs A)
    const int sj = nz + 2;
    const int plane = (ny + 2)*sj;
    const int nplanes = nx + 2;
-   double *sm = reinterpret_cast<double *>(smem_raw);
-   SOp *sops = reinterpret_cast<SOp *>(smem_raw + (size_t)nplanes*plane*8);
-   uint64_t *full = reinterpret_cast<uint64_t *>(sops + MAX_OPS);
+   const int tile = nplanes*plane;
+   // two tile buffers: while variable t is computed, the tile of t+1 is in flight
+   // and the finished tile of t-1 drains to global memory
+   double *buf0 = reinterpret_cast<double *>(smem_raw);
+   SOp *sops = reinterpret_cast<SOp *>(smem_raw + (size_t)2*tile*8);
+   uint64_t *full = reinterpret_cast<uint64_t *>(sops + MAX_OPS);   // [2]
 
    const int tid = threadIdx.x;
-   const int a = blockIdx.x%A.num_active;
-   const int vl = blockIdx.x/A.num_active;
-   const int v = A.var_start + vl;
-   const long long tile_off = (long long)v*A.var_stride + (long long)A.slots[a]*A.tile_stride;
-   const double *tin = A.pool_in + tile_off;
-   double *tout = A.pool_out + tile_off;
+   const int a = A.order[blockIdx.x%A.num_active];
+   const int grp = blockIdx.x/A.num_active;
+   const int v0 = A.var_start + grp*A.vpc;
+   const int nv = min(A.vpc, A.var_end - v0);
+   const long long slot_off = (long long)A.slots[a]*A.tile_stride;
 
    const int ob = A.begin[a];
    const int nops = A.begin[a + 1] - ob;
    if (tid == 0) {
-      mbar_init(full, 1);
+      mbar_init(&full[0], 1);
+      mbar_init(&full[1], 1);
       fence_barrier_init();
    }
    // stage the op table (one thread per op)
@@ -114,24 +147,27 @@ fused_kernel(const FusedArgs A)
       sops[tid] = s;
    }
    __syncthreads();
+   const uint32_t in_bytes = (uint32_t)nx*plane*8u;
    if (tid == 0) {
-      const uint32_t bytes = (uint32_t)nx*plane*8u;
-      mbar_arrive_expect_tx(full, bytes);
-      // planes 1..nx are one contiguous run; copy plane by plane (<= 64 KB each)
-      for (int p = 1; p <= nx; p++)
-         bulk_g2s(sm + (size_t)p*plane, tin + (size_t)p*plane, (uint32_t)plane*8u, full);
+      const double *tin = A.pool_in + (long long)v0*A.var_stride + slot_off;
+      mbar_arrive_expect_tx(&full[0], in_bytes);
+      for (int p = 1; p <= nx; p++)   // planes 1..nx, one bulk copy per plane
+         bulk_g2s(buf0 + (size_t)p*plane, tin + (size_t)p*plane, (uint32_t)plane*8u, &full[0]);
    }
 
-   // ---- halo gather: every load is issued before the wait on the bulk copy ----
+   // ---- decode this thread's share of the halo once; it is the same for every
+   // variable of the block (only the variable offset changes) ----
    const int last = nops - 1;
    const int E = nops > 0 ? sops[last].first + sops[last].e0*sops[last].e1*sops[last].e2 : 0;
-   double val[Q];
-   int dsto[Q];
+   // per halo cell: source offset (elements, from the variable's base; the host
+   // guarantees it fits 32 bits) and destination offset | op << 20 | mode << 26 |
+   // src_mem << 29
+   int soff[Q], dinfo[Q];
 #pragma unroll
    for (int q = 0; q < Q; q++) {
       const int e = tid + q*FUSED_THREADS;
-      dsto[q] = -1;
-      val[q] = 0.0;
+      soff[q] = 0;
+      dinfo[q] = -1;
       if (e < E) {
          int lo = 0, hi = last;
          while (lo < hi) {                       // last op with first <= e
@@ -143,24 +179,14 @@ fused_kernel(const FusedArgs A)
          const int c = r%s.e2; r /= s.e2;
          const int b = r%s.e1;
          const int aa = r/s.e1;
-         dsto[q] = s.dst_base + aa*s.ds0 + b*s.ds1 + c*s.ds2;
-         const double *base = (s.src_mem == BM_POOL)
-                                 ? A.pool_in + (long long)v*A.var_stride
-                                 : A.recv[s.src_mem - BM_BUF0] + (long long)(v - A.buf_var0)*s.src_vs;
-         base += s.src_base;
+         const int dsto = s.dst_base + aa*s.ds0 + b*s.ds1 + c*s.ds2;
          const int mode = s.mode;
-         if (mode == FM_COPY) {
-            val[q] = __ldg(base + (long long)aa*s.ss0 + b*s.ss1 + c*s.ss2);
-         } else if (mode == FM_PROLONG || mode == FM_REPL) {
-            const double x = __ldg(base + (long long)(aa >> 1)*s.ss0 + (b >> 1)*s.ss1 + (c >> 1)*s.ss2);
-            val[q] = mode == FM_PROLONG ? x/4.0 : x;
-         } else {   // FM_SUM4, left to right, slow index outer (comm.c:1626-1629)
-            const double *p = base + (long long)(2*aa)*s.ss0 + (2*b)*s.ss1 + (2*c)*s.ss2;
-            double t = __ldg(p) + __ldg(p + s.F);
-            t += __ldg(p + s.S);
-            t += __ldg(p + s.S + s.F);
-            val[q] = t;
-         }
+         long long o;
+         if (mode == FM_COPY) o = (long long)aa*s.ss0 + b*s.ss1 + c*s.ss2;
+         else if (mode == FM_SUM4) o = (long long)(2*aa)*s.ss0 + (2*b)*s.ss1 + (2*c)*s.ss2;
+         else o = (long long)(aa >> 1)*s.ss0 + (b >> 1)*s.ss1 + (c >> 1)*s.ss2;
+         soff[q] = (int)(s.src_base + o);
+         dinfo[q] = dsto | (lo << 20) | (mode << 26) | (s.src_mem << 29);
       }
    }
 
@@ -177,59 +203,145 @@ fused_kernel(const FusedArgs A)
       off[q] = (j + 1)*sj + (cc - j*nz) + 1;
    }
 
-   mbar_wait(full, 0);
-#pragma unroll
-   for (int q = 0; q < Q; q++)
-      if (dsto[q] >= 0) {
-         sm[dsto[q]] = val[q];
-         tout[dsto[q]] = val[q];
-      }
-   __syncthreads();
+   // 27-point path: thread -> (chunk of planes, 2x2 patch)
+   const int hk = nz >> 1, groups = (ny >> 1)*hk;
+   const int pchunk = tid/groups, pg = tid - pchunk*groups;
+   const bool pact = STENCIL != 7 && pchunk*A.chunk < nx;
+   const int poff = (2*(pg/hk))*sj + 2*(pg%hk);   // row 2jp, column 2kp: the ring's corner
 
-   // ---- stencil: march along i, two previous plane contributions in registers --
-   double prev[CPT], cur[CPT];
+   for (int t = 0; t < nv; t++) {
+      const int v = v0 + t;
+      double *sm = buf0 + (size_t)(t & 1)*tile;
+      // ---- halo gather for variable v: every load is issued before the wait on
+      // the bulk copy, so both latencies overlap ----
+      double val[Q];
+      const double *pin = A.pool_in + (long long)v*A.var_stride;
 #pragma unroll
-   for (int q = 0; q < CPT; q++) {
-      if (STENCIL == 7) {
-         prev[q] = sm[off[q]];
-         cur[q] = sm[plane + off[q]];
-      } else {
-         prev[q] = plane_sum9(sm + off[q], sj);
-         cur[q] = plane_sum9(sm + plane + off[q], sj);
-      }
-   }
-   for (int i = 1; i <= nx; i++) {
-      const double *pc = sm + (size_t)i*plane;
-      const double *pn = pc + plane;
-      double *out = tout + (size_t)i*plane;
-#pragma unroll
-      for (int q = 0; q < CPT; q++) {
-         double r;
-         if (STENCIL == 7) {
-            const double *c = pc + off[q];
-            const double e = pn[off[q]];
-            double s = prev[q] + c[-sj];           // W + S
-            s += c[-1];                            // + D
-            s += cur[q];                           // + C
-            s += c[1];                             // + U
-            s += c[sj];                            // + N
-            s += e;                                // + E
-            r = div_const<7>(s);
-            prev[q] = cur[q];
-            cur[q] = e;
-         } else {
-            const double nxt = plane_sum9(pn + off[q], sj);
-            r = div_const<27>((prev[q] + cur[q]) + nxt);
-            prev[q] = cur[q];
-            cur[q] = nxt;
+      for (int q = 0; q < Q; q++) {
+         val[q] = 0.0;
+         if (dinfo[q] >= 0) {
+            const int mode = (dinfo[q] >> 26) & 7, mem = dinfo[q] >> 29, op = (dinfo[q] >> 20) & 63;
+            const double *p = pin;
+            if (mem != BM_POOL)
+               p = A.recv[mem - BM_BUF0] + (long long)(v - A.buf_var0)*sops[op].src_vs;
+            p += soff[q];
+            if (mode == FM_COPY || mode == FM_REPL)
+               val[q] = __ldg(p);
+            else if (mode == FM_PROLONG)
+               val[q] = __ldg(p)/4.0;
+            else {   // FM_SUM4, left to right, slow index outer (comm.c:1626-1629)
+               const int S = sops[op].S, F = sops[op].F;
+               double x = __ldg(p) + __ldg(p + F);
+               x += __ldg(p + S);
+               x += __ldg(p + S + F);
+               val[q] = x;
+            }
          }
-         if (live[q]) out[off[q]] = r;
+      }
+      mbar_wait(&full[t & 1], (uint32_t)((t >> 1) & 1));
+#pragma unroll
+      for (int q = 0; q < Q; q++)
+         if (dinfo[q] >= 0) sm[dinfo[q] & 0xfffff] = val[q];
+      __syncthreads();
+      // prefetch the next variable's tile into the other buffer once the bulk store
+      // that last read that buffer (variable t-1) has drained
+      if (tid == 0 && t + 1 < nv) {
+         bulk_wait_read0();
+         double *nb = buf0 + (size_t)((t + 1) & 1)*tile;
+         const double *tin = A.pool_in + (long long)(v + 1)*A.var_stride + slot_off;
+         mbar_arrive_expect_tx(&full[(t + 1) & 1], in_bytes);
+         for (int p = 1; p <= nx; p++)
+            bulk_g2s(nb + (size_t)p*plane, tin + (size_t)p*plane, (uint32_t)plane*8u,
+                     &full[(t + 1) & 1]);
+      }
+
+      // ---- stencil.  The new value of a plane replaces the old one in shared
+      // memory once every thread has finished reading that plane (one barrier per
+      // step); the finished tile -- gathered ghosts + new interior -- then leaves
+      // as ONE bulk copy.
+      if (STENCIL == 7) {
+         // march the (j,k) columns along i, W and C in registers
+         double prev[CPT], cur[CPT];
+#pragma unroll
+         for (int q = 0; q < CPT; q++) {
+            prev[q] = sm[off[q]];
+            cur[q] = sm[plane + off[q]];
+         }
+         for (int i = 1; i <= nx; i++) {
+            double *pc = sm + (size_t)i*plane;
+            const double *pn = pc + plane;
+            double r[CPT];
+#pragma unroll
+            for (int q = 0; q < CPT; q++) {
+               const double *c = pc + off[q];
+               const double e = pn[off[q]];
+               double s = prev[q] + c[-sj];           // W + S
+               s += c[-1];                            // + D
+               s += cur[q];                           // + C
+               s += c[1];                             // + U
+               s += c[sj];                            // + N
+               s += e;                                // + E
+               r[q] = div_const<7>(s);
+               prev[q] = cur[q];
+               cur[q] = e;
+            }
+            __syncthreads();       // plane i has been read by everyone
+#pragma unroll
+            for (int q = 0; q < CPT; q++)
+               if (live[q]) pc[off[q]] = r[q];
+         }
+      } else {
+         // thread = (chunk of i-planes, 2x2 patch of columns); sb/sm/sf of
+         // stencil.c:111-138 are the plane sums of planes i-1, i, i+1
+         const int CH = A.chunk;
+         const int i0 = pchunk*CH + 1;
+         const int ilast = min(nx, i0 + CH - 1);
+         double prev[4], cur[4], lst[4];
+         if (pact) {
+            const double *pp = sm + poff;
+            patch_sums(pp + (size_t)(i0 - 1)*plane, sj, prev);
+            patch_sums(pp + (size_t)i0*plane, sj, cur);
+            // plane ilast+1 is the next chunk's first output plane: read it now
+            patch_sums(pp + (size_t)(ilast + 1)*plane, sj, lst);
+         }
+         for (int s = 0; s < CH; s++) {
+            const int i = i0 + s;
+            double r[4];
+            const bool on = pact && i <= ilast;
+            if (on) {
+               double nxt[4];
+               if (i == ilast) {
+#pragma unroll
+                  for (int u = 0; u < 4; u++) nxt[u] = lst[u];
+               } else
+                  patch_sums(sm + poff + (size_t)(i + 1)*plane, sj, nxt);
+#pragma unroll
+               for (int u = 0; u < 4; u++) {
+                  r[u] = div_const<27>((prev[u] + cur[u]) + nxt[u]);
+                  prev[u] = cur[u];
+                  cur[u] = nxt[u];
+               }
+            }
+            __syncthreads();       // plane i has been read by everyone
+            if (on) {
+               double *o = sm + poff + (size_t)i*plane + sj + 1;
+               o[0] = r[0]; o[1] = r[1];
+               o[sj] = r[2]; o[sj + 1] = r[3];
+            }
+         }
+      }
+      fence_proxy_async();
+      __syncthreads();
+      if (tid == 0) {
+         bulk_s2g(A.pool_out + (long long)v*A.var_stride + slot_off, sm, (uint32_t)tile*8u);
+         bulk_commit();
       }
    }
+   if (tid == 0) bulk_wait_read0();
 }
 
 struct FusedPlan {
-   int cpt, q, smem;
+   int cpt, q, smem, chunk;
    bool ok;
 };
 
@@ -243,8 +355,14 @@ FusedPlan make_plan(const Geometry &g)
    const int halo = g.tile - g.n[0]*g.n[1]*g.n[2];
    const int q = (halo + FUSED_THREADS - 1)/FUSED_THREADS;
    p.q = q <= 4 ? 4 : (q <= 8 ? 8 : (q <= 12 ? 12 : 16));
-   p.smem = g.tile*8 + MAX_OPS*(int)sizeof(SOp) + 16;
-   p.ok = p.cpt <= 4 && q <= 16 && p.smem <= 110*1024;
+   p.smem = 2*g.tile*8 + MAX_OPS*(int)sizeof(SOp) + 32;
+   // 27-point path: smallest chunk of planes such that (patches x chunks) fits the CTA
+   const int groups = (g.n[1]/2)*(g.n[2]/2);
+   p.chunk = 1;
+   while (groups*((g.n[0] + p.chunk - 1)/p.chunk) > FUSED_THREADS && p.chunk < g.n[0]) p.chunk++;
+   p.ok = p.cpt <= 4 && q <= 16 && p.smem <= 113*1024 &&                  // two CTAs per SM
+          groups*((g.n[0] + p.chunk - 1)/p.chunk) <= FUSED_THREADS &&
+          g.tile < (1 << 20) && g.var_stride < (1LL << 31);
    return p;
 }
 
@@ -287,32 +405,39 @@ bool fused_configure(const Geometry &g, std::string &err)
 }
 
 void launch_fused(const double *pool_in, double *pool_out, const Geometry &g, const int *d_slots,
-                  int num_active, const BoxOp *d_ops, const int *d_begin,
+                  const int *d_order, int num_active, const BoxOp *d_ops, const int *d_begin,
                   const double *const recv[3], int var_start, int num_vars, int buf_var0,
                   int stencil, cudaStream_t s)
 {
    if (num_active <= 0 || num_vars <= 0) return;
    const FusedPlan p = make_plan(g);
    FusedArgs A;
-   A.pool_in = pool_in; A.pool_out = pool_out; A.slots = d_slots;
+   A.pool_in = pool_in; A.pool_out = pool_out; A.slots = d_slots; A.order = d_order;
    A.ops = d_ops; A.begin = d_begin;
    for (int d = 0; d < 3; d++) A.recv[d] = recv ? recv[d] : nullptr;
    A.tile_stride = g.tile_stride; A.var_stride = g.var_stride;
    A.num_active = num_active; A.buf_var0 = buf_var0;
    A.nx = g.n[0]; A.ny = g.n[1]; A.nz = g.n[2];
-   const int max_vars = (int)(((1LL << 31) - 1)/num_active);
-   for (int v0 = 0; v0 < num_vars; v0 += max_vars) {
-      const int nv = (num_vars - v0 < max_vars) ? num_vars - v0 : max_vars;
-      const unsigned grid = (unsigned)((long long)num_active*nv);
-      A.var_start = var_start + v0;
+   A.chunk = p.chunk;
+   // one CTA per (block, group of `vpc` variables)
+   static int vpc_env = -1;
+   if (vpc_env < 0) {
+      const char *e = getenv("MAMR_VPC");
+      vpc_env = e ? atoi(e) : 0;
+   }
+   A.vpc = vpc_env > 0 ? vpc_env : 8;
+   if (A.vpc > num_vars) A.vpc = num_vars;
+   A.var_start = var_start;
+   A.var_end = var_start + num_vars;
+   const long long groups = (num_vars + A.vpc - 1)/A.vpc;
+   const unsigned grid = (unsigned)((long long)num_active*groups);
 #define X(C, QQ)                                                                       \
    if (p.cpt == C && p.q == QQ) {                                                      \
       if (stencil == 7) fused_kernel<7, C, QQ><<<grid, FUSED_THREADS, p.smem, s>>>(A); \
       else fused_kernel<27, C, QQ><<<grid, FUSED_THREADS, p.smem, s>>>(A);             \
    }
-      MAMR_FUSED_VARIANTS(X)
+   MAMR_FUSED_VARIANTS(X)
 #undef X
-   }
 }
 
 // ---------------------------------------------------------------------------

@@ -53,6 +53,28 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint3
       : "memory");
 }
 
+// 1-D bulk TMA copy shared -> global (bulk async-group completion)
+__device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, uint32_t bytes)
+{
+   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                "r"(smem_u32(smem_src)), "r"(bytes)
+                : "memory");
+}
+
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+
+// wait until the bulk stores of this thread have finished READING shared memory
+__device__ __forceinline__ void bulk_wait_read0()
+{
+   asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// make this thread's generic-proxy shared-memory writes visible to the async proxy (TMA)
+__device__ __forceinline__ void fence_proxy_async()
+{
+   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
 // x / D for D = 7.0 or 27.0 with the result of an IEEE-754 division, in three
 // FP64 pipe operations instead of the ~20-instruction generic division sequence.
 // With y = RN(1/D): q = RN(x*y), r = x - D*q (exact in the FMA), q' = RN(q + r*y).

@@ -209,39 +209,54 @@ fused_kernel(const FusedArgs A)
    const bool pact = STENCIL != 7 && pchunk*A.chunk < nx;
    const int poff = (2*(pg/hk))*sj + 2*(pg%hk);   // row 2jp, column 2kp: the ring's corner
 
-   for (int t = 0; t < nv; t++) {
-      const int v = v0 + t;
-      double *sm = buf0 + (size_t)(t & 1)*tile;
-      // ---- halo gather for variable v: every load is issued before the wait on
-      // the bulk copy, so both latencies overlap ----
-      double val[Q];
+   // pull this thread's halo cells of variable v into tile buffer `dst`
+   auto gather = [&](int v, double *dst) {
       const double *pin = A.pool_in + (long long)v*A.var_stride;
 #pragma unroll
       for (int q = 0; q < Q; q++) {
-         val[q] = 0.0;
          if (dinfo[q] >= 0) {
             const int mode = (dinfo[q] >> 26) & 7, mem = dinfo[q] >> 29, op = (dinfo[q] >> 20) & 63;
             const double *p = pin;
             if (mem != BM_POOL)
                p = A.recv[mem - BM_BUF0] + (long long)(v - A.buf_var0)*sops[op].src_vs;
             p += soff[q];
+            double *d = dst + (dinfo[q] & 0xfffff);
             if (mode == FM_COPY || mode == FM_REPL)
-               val[q] = __ldg(p);
+               cp_async8(d, p);
             else if (mode == FM_PROLONG)
-               val[q] = __ldg(p)/4.0;
+               *d = __ldg(p)/4.0;
             else {   // FM_SUM4, left to right, slow index outer (comm.c:1626-1629)
                const int S = sops[op].S, F = sops[op].F;
                double x = __ldg(p) + __ldg(p + F);
                x += __ldg(p + S);
                x += __ldg(p + S + F);
-               val[q] = x;
+               *d = x;
             }
          }
       }
-      mbar_wait(&full[t & 1], (uint32_t)((t >> 1) & 1));
-#pragma unroll
-      for (int q = 0; q < Q; q++)
-         if (dinfo[q] >= 0) sm[dinfo[q] & 0xfffff] = val[q];
+   };
+   bool pre = false;   // this thread's halo of the coming variable is already on its way
+   // called once per variable from inside the stencil loop
+   auto prefetch_halo = [&](int t) {
+      if (t + 1 < nv && !pre && mbar_test(&full[(t + 1) & 1], (uint32_t)(((t + 1) >> 1) & 1))) {
+         gather(v0 + t + 1, buf0 + (size_t)((t + 1) & 1)*tile);
+         pre = true;
+      }
+   };
+
+   for (int t = 0; t < nv; t++) {
+      const int v = v0 + t;
+      double *sm = buf0 + (size_t)(t & 1)*tile;
+      // ---- halo gather for variable v.  Plain copies go global -> shared as
+      // 8-byte cp.async (no registers, asynchronous); they are normally issued
+      // during the PREVIOUS variable's stencil, as soon as this tile's bulk copy
+      // has landed (it would otherwise overwrite the ghost cells afterwards).
+      if (!pre) {
+         mbar_wait(&full[t & 1], (uint32_t)((t >> 1) & 1));
+         gather(v, sm);
+      }
+      pre = false;
+      cp_async_wait_all();
       __syncthreads();
       // prefetch the next variable's tile into the other buffer once the bulk store
       // that last read that buffer (variable t-1) has drained
@@ -289,6 +304,7 @@ fused_kernel(const FusedArgs A)
 #pragma unroll
             for (int q = 0; q < CPT; q++)
                if (live[q]) pc[off[q]] = r[q];
+            if (i == (nx >> 1) || i == nx) prefetch_halo(t);
          }
       } else {
          // thread = (chunk of i-planes, 2x2 patch of columns); sb/sm/sf of
@@ -328,6 +344,7 @@ fused_kernel(const FusedArgs A)
                o[0] = r[0]; o[1] = r[1];
                o[sj] = r[2]; o[sj + 1] = r[3];
             }
+            if (s == (CH >> 1) || s == CH - 1) prefetch_halo(t);
          }
       }
       fence_proxy_async();

@@ -42,6 +42,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
       : "memory");
 }
 
+// non-blocking probe of an mbarrier phase
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
+{
+   uint32_t ok;
+   asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, P1;\n"
+      "}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+   return ok != 0;
+}
+
+// 8-byte asynchronous copy global -> shared (SASS LDGSTS): no register staging
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc)
+{
+   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc)
+                : "memory");
+}
+
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // 1-D bulk TMA copy global -> shared, completion counted in bytes on `bar`
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes,
                                          uint64_t *bar)

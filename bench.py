@@ -338,7 +338,7 @@ def run_ours(args):
         traffic = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = tr.get(f"{args.workload}:{B}", {}).get("stencil_bytes_per_launch")
+            traffic = tr.get(f"{args.workload}:{B}", {}).get("fused_bytes_per_launch")
         except Exception:
             pass
         stage_gbs = value/world*bpu["stage"]/1e9
@@ -352,7 +352,7 @@ def run_ours(args):
                        "stencil": stencil, "rank_grid": [npx, npy, npz],
                        "bytes_per_gpu": d.pool_bytes(),
                        "cache": "inputs (7.6 GB/GPU at the default size) exceed the 126 MB L2"},
-            "roofline": {"bound": "hbm", "kernel": f"stencil_kernel<{stencil}>",
+            "roofline": {"bound": "hbm", "kernel": f"fused_kernel<{stencil}> (halo gather + stencil)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved/peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": st_bytes,

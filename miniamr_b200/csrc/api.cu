@@ -113,6 +113,8 @@ struct mamr_ctx {
    bool fused_geom = false;     // the tile fits the fused kernel
    bool use_fused = true;       // MAMR_NO_FUSED=1 forces the split path
    HaloPlan plan[6];
+   std::vector<BoxOp> pack[6][3];       // multi-GPU: send-buffer fill per phase
+   BoxOp *d_pack[6][3] = {};
    bool plan_built[6] = {false, false, false, false, false, false};
    BoxOp *d_hops[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
    int *d_hbegin[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -560,8 +562,10 @@ int exchange_dir(mamr_ctx *c, int d)
 }
 
 // Execute one direction-phased comm() on variables [start, start+num) in place in
-// their current pool (all in the same pool): the split path.
-int comm_split(mamr_ctx *c, int start, int num, int ord)
+// their current pool (all in the same pool): the split path.  buf_var0 is the
+// first variable of the comm() call (variable 0 of the message buffers); with
+// exchange == false the receive buffers already hold this call's messages.
+int comm_split(mamr_ctx *c, int start, int num, int ord, int buf_var0, bool exchange)
 {
    if (c->ops_dirty) CK(build_ops(c));
    if (c->have_partners && !c->nccl)
@@ -573,15 +577,16 @@ int comm_split(mamr_ctx *c, int start, int num, int ord)
       if (!c->ops_main[d].empty() && num > 0) {
          KTimer t(c, KC_GHOST);
          launch_ghost(c->d_ops + c->off_main[d], (int)c->ops_main[d].size(), pool, c->d_send[d],
-                      c->d_recv[d], c->g.var_stride, start, num, c->stream);
+                      c->d_recv[d], c->g.var_stride, start, num, buf_var0, c->stream);
          c->cnt.kernel_launches++;
       }
       if (!L.partner.empty()) {
-         CK(exchange_dir(c, d));
+         if (exchange) CK(exchange_dir(c, d));
          if (!c->ops_unpack[d].empty() && num > 0) {
             KTimer t(c, KC_GHOST);
             launch_ghost(c->d_ops + c->off_unpack[d], (int)c->ops_unpack[d].size(), pool,
-                         c->d_send[d], c->d_recv[d], c->g.var_stride, start, num, c->stream);
+                         c->d_send[d], c->d_recv[d], c->g.var_stride, start, num, buf_var0,
+                         c->stream);
             c->cnt.kernel_launches++;
          }
       }
@@ -590,15 +595,14 @@ int comm_split(mamr_ctx *c, int start, int num, int ord)
    return MAMR_OK;
 }
 
-// make the deferred comm() of variables [v0, v0+n) real (ghost cells in memory)
+// make the deferred comm() of variables [v0, v0+n) real (ghost cells in memory).
+// Off-rank faces were already exchanged when the comm() was deferred.
 int materialize_comm(mamr_ctx *c, int v0, int n)
 {
    for (const Run &r : runs_of(c, v0, n, true)) {
       const int ord = c->pc_ord[r.start];
       if (ord < 0) continue;
-      if (c->have_partners)
-         return fail(MAMR_EINVAL, "internal: deferred comm with off-rank partners");
-      CK(comm_split(c, r.start, r.num, ord));
+      CK(comm_split(c, r.start, r.num, ord, c->pc_start[r.start], false));
       for (int v = r.start; v < r.start + r.num; v++) c->pc_ord[v] = -1;
    }
    return MAMR_OK;
@@ -621,6 +625,8 @@ int ensure_plan(mamr_ctx *c, int ord)
       P.ok = false;
       P.why = "more than 64 halo ops on one block";
    }
+   for (int o = 0; o < 3 && P.ok && c->have_partners; o++)
+      if (!build_pack_plan(in, o, c->pack[ord][o], P.why)) P.ok = false;
    c->plan_built[ord] = true;
    if (!P.ok) return MAMR_OK;
    CU(cudaStreamSynchronize(c->stream));
@@ -635,6 +641,15 @@ int ensure_plan(mamr_ctx *c, int ord)
                          cudaMemcpyHostToDevice, c->stream));
    CU(cudaMemcpyAsync(c->d_hbegin[ord], P.begin.data(), P.begin.size()*sizeof(int),
                       cudaMemcpyHostToDevice, c->stream));
+   for (int o = 0; o < 3; o++) {
+      if (c->d_pack[ord][o]) CU(cudaFree(c->d_pack[ord][o]));
+      c->d_pack[ord][o] = nullptr;
+      const std::vector<BoxOp> &K = c->pack[ord][o];
+      if (!c->have_partners || K.empty()) continue;
+      CU(cudaMalloc(&c->d_pack[ord][o], K.size()*sizeof(BoxOp)));
+      CU(cudaMemcpyAsync(c->d_pack[ord][o], K.data(), K.size()*sizeof(BoxOp),
+                         cudaMemcpyHostToDevice, c->stream));
+   }
    CU(cudaStreamSynchronize(c->stream));
    return MAMR_OK;
 }
@@ -643,8 +658,8 @@ int ensure_plan(mamr_ctx *c, int ord)
 int fused_ready(mamr_ctx *c, int ord, bool *yes)
 {
    *yes = false;
-   if (!c->use_fused || !c->fused_geom || c->have_partners || c->num_active == 0)
-      return MAMR_OK;
+   if (!c->use_fused || !c->fused_geom || c->num_active == 0) return MAMR_OK;
+   if (c->have_partners && !c->nccl) return MAMR_OK;   // comm_split reports the error
    CK(ensure_plan(c, ord));
    *yes = c->plan[ord].ok;
    return MAMR_OK;
@@ -832,7 +847,11 @@ void mamr_destroy(mamr_ctx *c)
    if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
    cudaFree(c->pool[0]);
    cudaFree(c->pool[1]);
-   for (int o = 0; o < 6; o++) { cudaFree(c->d_hops[o]); cudaFree(c->d_hbegin[o]); }
+   for (int o = 0; o < 6; o++) {
+      cudaFree(c->d_hops[o]);
+      cudaFree(c->d_hbegin[o]);
+      for (int q = 0; q < 3; q++) cudaFree(c->d_pack[o][q]);
+   }
    cudaFree(c->d_slots);
    cudaFree(c->d_order);
    cudaFree(c->d_ops);
@@ -1074,12 +1093,35 @@ int mamr_comm(mamr_ctx *c, int start, int num_comm, int stage)
    if (defer) {
       // the fused kernel performs this exchange when the stencil of the variables
       // is launched; anything else that needs the ghost cells materialises it
+      if (c->have_partners && num_comm > 0) {
+         // the message buffers are about to be reused: an older deferred comm()
+         // that still needs them becomes real first
+         CK(materialize_comm(c, 0, c->p.num_vars));
+         // off-rank faces: per phase, fill the send buffers from resolved origins
+         // (pack_face, comm.c:254-401) and exchange them (comm.c:71-84, 120-151)
+         double *send[3] = { c->d_send[0], c->d_send[1], c->d_send[2] };
+         const double *recv[3] = { c->d_recv[0], c->d_recv[1], c->d_recv[2] };
+         for (int o = 0; o < 3; o++) {
+            const int d = kPerm[ord][o];
+            if (c->cl[d].partner.empty()) continue;
+            for (const Run &r : runs_of(c, start, num_comm, false)) {
+               KTimer t(c, KC_GHOST);
+               launch_boxops(c->d_pack[ord][o], (int)c->pack[ord][o].size(), vpool(c, r.start),
+                             vpool(c, r.start), c->g.var_stride, send, recv, r.start, r.num, start,
+                             c->stream);
+               c->cnt.kernel_launches++;
+            }
+            CK(exchange_dir(c, d));
+         }
+         CU(cudaGetLastError());
+      }
       for (int v = start; v < start + num_comm; v++) {
          c->pc_ord[v] = (signed char)ord;
          c->pc_start[v] = start;
       }
    } else
-      for (const Run &r : runs_of(c, start, num_comm, false)) CK(comm_split(c, r.start, r.num, ord));
+      for (const Run &r : runs_of(c, start, num_comm, false))
+         CK(comm_split(c, r.start, r.num, ord, start, true));
    for (int d = 0; d < 3; d++) {
       c->cnt.counter_same[d] += c->n_same[d];
       c->cnt.counter_diff[d] += c->n_diff[d];

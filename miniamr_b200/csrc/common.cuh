@@ -110,7 +110,7 @@ struct RefineOp {
 // kernels (launchers) -------------------------------------------------------
 void launch_ghost(const FaceOp *d_ops, int n_ops, double *pool, double *send_buf,
                   const double *recv_buf, long long pool_var_stride, int start,
-                  int num, cudaStream_t s);
+                  int num, int buf_var0, cudaStream_t s);
 void launch_stencil(double *pool, const Geometry &g, const int *d_slots,
                     int num_active, int var_start, int num_vars, int stencil,
                     cudaStream_t s);

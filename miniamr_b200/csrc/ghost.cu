@@ -40,15 +40,18 @@ __device__ __forceinline__ double face_value(const double *__restrict__ src, int
 __global__ void __launch_bounds__(128)
 ghost_phase_kernel(const FaceOp *__restrict__ ops, double *__restrict__ pool,
                    double *__restrict__ send_buf, const double *__restrict__ recv_buf,
-                   long long pool_var_stride, int start)
+                   long long pool_var_stride, int start, int buf_off)
 {
    const FaceOp op = ops[blockIdx.x];
    const int vloc = blockIdx.y;
-   double *dst = ((op.mem & MEM_DST_SEND) ? send_buf : pool + (long long)start*pool_var_stride) +
-                 op.dst_base + (long long)vloc*op.dst_vs;
-   const double *src = ((op.mem & MEM_SRC_RECV) ? recv_buf
-                                                : pool + (long long)start*pool_var_stride) +
-                       op.src_base + (long long)vloc*op.src_vs;
+   // message buffers are indexed from the first variable of the comm() call
+   double *dst = (op.mem & MEM_DST_SEND)
+                    ? send_buf + op.dst_base + (long long)(vloc + buf_off)*op.dst_vs
+                    : pool + (long long)start*pool_var_stride + op.dst_base + (long long)vloc*op.dst_vs;
+   const double *src = (op.mem & MEM_SRC_RECV)
+                          ? recv_buf + op.src_base + (long long)(vloc + buf_off)*op.src_vs
+                          : pool + (long long)start*pool_var_stride + op.src_base +
+                               (long long)vloc*op.src_vs;
    const int cells = op.Ns*op.Nf;
    const int Nf = op.Nf;
    for (int c = threadIdx.x; c < cells; c += blockDim.x) {
@@ -67,13 +70,13 @@ ghost_phase_kernel(const FaceOp *__restrict__ ops, double *__restrict__ pool,
 
 void launch_ghost(const FaceOp *d_ops, int n_ops, double *pool, double *send_buf,
                   const double *recv_buf, long long pool_var_stride, int start, int num,
-                  cudaStream_t s)
+                  int buf_var0, cudaStream_t s)
 {
    if (n_ops <= 0 || num <= 0) return;
    // gridDim.x can hold 2^31-1 ops; gridDim.y (variables) is limited to 65535
    dim3 grid((unsigned)n_ops, (unsigned)num);
    ghost_phase_kernel<<<grid, 128, 0, s>>>(d_ops, pool, send_buf, recv_buf,
-                                           pool_var_stride, start);
+                                           pool_var_stride, start, start - buf_var0);
 }
 
 }  // namespace mamr

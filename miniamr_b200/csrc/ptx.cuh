@@ -42,6 +42,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
       : "memory");
 }
 
+// named barrier over `count` threads (a multiple of 32); id 0 is __syncthreads()
+__device__ __forceinline__ void named_bar_sync(int id, int count)
+{
+   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
 // non-blocking probe of an mbarrier phase
 __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity)
 {

@@ -1,0 +1,45 @@
+"""N > 1 on real GPUs: blocks sharded over ranks, ghost faces over NCCL.  Needs
+at least 2 GPUs (run with `gpurun --gpus 2`); skipped otherwise."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+CASES = [
+    dict(np=[2, 1, 1], n=[4, 6, 8], b=[2, 2, 2], vars=3, stencil=7, stages=3, seed=1, check_comm=1),
+    dict(np=[2, 1, 1], n=[4, 6, 8], b=[2, 3, 2], vars=3, stencil=27, stages=3, seed=2, check_comm=1),
+    dict(np=[1, 2, 1], n=[6, 4, 4], b=[2, 2, 3], vars=4, stencil=27, stages=4, seed=3, comm_vars=3),
+    dict(np=[1, 1, 2], n=[4, 4, 6], b=[3, 2, 2], vars=2, stencil=27, stages=7, seed=4, permute=1),
+    dict(np=[1, 1, 2], n=[16, 16, 16], b=[2, 2, 2], vars=2, stencil=27, stages=2, seed=5),
+    dict(np=[2, 1, 1], n=[10, 10, 10], b=[2, 2, 2], vars=5, stencil=7, stages=3, seed=6, comm_vars=2),
+]
+
+
+@pytest.mark.parametrize("fused", [1, 0])
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_two_ranks_match_single_rank_oracle(case, fused):
+    if ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    cfg = CASES[case]
+    env = dict(os.environ)
+    env["MAMR_NO_FUSED"] = "0" if fused else "1"
+    port = 29600 + case*2 + fused
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port),
+           os.path.join(ROOT, "tests", "mgpu_worker.py"), json.dumps(cfg)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

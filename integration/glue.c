@@ -1,0 +1,391 @@
+/* Reference-side binding of libminiamr_b200.so (include/miniamr_b200.h).
+ *
+ * This file is compiled TOGETHER WITH THE UNMODIFIED REFERENCE host sources
+ * (main.c driver.c init.c refine.c move.c block.c rcb.c sfc.c comm_util.c
+ * comm_refine.c comm_parent.c comm_block.c profile.c plot.c util.c, taken from
+ * where they lie) and REPLACES the four files of the stage hot path:
+ *
+ *     stencil.c   -> stencil_driver(), stencil_calc()        (stencil.c:43-145)
+ *     comm.c      -> comm()                                  (comm.c:42-242)
+ *     check_sum.c -> check_sum()                             (check_sum.c:36-65)
+ *     pack.c      -> pack_block(), unpack_block()            (pack.c:34-108)
+ *
+ * with thin calls into the C ABI.  The three places where the reference touches
+ * block arrays in line are intercepted at link time, without editing a line of
+ * the reference (ld --wrap):
+ *
+ *     init()               init.c:484-495 fills blocks[].array on the host; the
+ *                          first hot-path call uploads every active block
+ *     split_blocks()       block.c:161-173: the topology part runs unchanged, the
+ *                          data copy is replayed on the device (mamr_split_block)
+ *     consolidate_blocks() block.c:418-430: likewise (mamr_consolidate_block)
+ *     refine()             marks the device topology stale (H4)
+ *
+ * blocks[].array stays allocated by the reference's allocate() (main.c:429-450)
+ * but is only a staging area: block data lives in the device pool.
+ * mamr_glue_sync_host() copies it back for anything that wants to look.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mpi.h>
+
+#include "block.h"
+#include "comm.h"
+#include "timer.h"
+#include "proto.h"
+
+#include "miniamr_b200.h"
+
+static mamr_ctx *G;
+static int topo_dirty = 1;      /* device descriptors older than blocks[]/comm lists */
+static int host_fresh = 1;      /* blocks[].array holds data the device has not seen */
+static mamr_counters seen;      /* counters already added to the reference's globals */
+static double *stage_tile;      /* one block, [var][i][j][k] contiguous            */
+
+static void die(const char *where)
+{
+   printf("%d ERROR: miniamr_b200 %s: %s\n", my_pe, where, mamr_last_error());
+   fflush(stdout);
+   exit(-1);                    /* the reference's own error convention, comm.c:199-200 */
+}
+
+#define OK(call, where) do { if ((call) != MAMR_OK) die(where); } while (0)
+
+static size_t tile_doubles(void)
+{
+   return (size_t)(x_block_size+2)*(y_block_size+2)*(z_block_size+2);
+}
+
+static void ensure_ctx(void)
+{
+   mamr_params p;
+   if (G) return;
+   memset(&p, 0, sizeof p);
+   p.nx = x_block_size; p.ny = y_block_size; p.nz = z_block_size;
+   p.num_vars = num_vars; p.comm_vars = comm_vars; p.max_blocks = max_num_blocks;
+   p.stencil = stencil; p.code = code; p.permute = permute;
+   p.device = -1; p.rank = my_pe; p.num_ranks = num_pes;
+   if (getenv("MAMR_DEVICE")) p.device = atoi(getenv("MAMR_DEVICE"));
+   OK(mamr_create(&p, &G), "create");
+   stage_tile = (double *) malloc((size_t)num_vars*tile_doubles()*sizeof(double));
+   memset(&seen, 0, sizeof seen);
+}
+
+/* jagged blocks[n].array <-> contiguous staging tile */
+static void gather_host(int n, double *t)
+{
+   int v, i, j;
+   size_t l = 0, row = (size_t)(z_block_size+2);
+   for (v = 0; v < num_vars; v++)
+      for (i = 0; i <= x_block_size+1; i++)
+         for (j = 0; j <= y_block_size+1; j++, l += row)
+            memcpy(t + l, blocks[n].array[v][i][j], row*sizeof(double));
+}
+
+static void scatter_host(int n, const double *t)
+{
+   int v, i, j;
+   size_t l = 0, row = (size_t)(z_block_size+2);
+   for (v = 0; v < num_vars; v++)
+      for (i = 0; i <= x_block_size+1; i++)
+         for (j = 0; j <= y_block_size+1; j++, l += row)
+            memcpy(blocks[n].array[v][i][j], t + l, row*sizeof(double));
+}
+
+static void upload_host_blocks(void)
+{
+   int in, n;
+   if (!host_fresh) return;
+   for (in = 0; in < sorted_index[num_refine+1]; in++) {
+      n = sorted_list[in].n;
+      gather_host(n, stage_tile);
+      OK(mamr_upload_block(G, n, stage_tile), "upload_block");
+   }
+   host_fresh = 0;
+}
+
+/* device -> blocks[].array for every active block (plot, debugging, tests) */
+void mamr_glue_sync_host(void)
+{
+   int in, n;
+   if (!G || host_fresh) return;
+   for (in = 0; in < sorted_index[num_refine+1]; in++) {
+      n = sorted_list[in].n;
+      OK(mamr_download_block(G, n, stage_tile), "download_block");
+      scatter_host(n, stage_tile);
+   }
+}
+
+/* what the path reads through the globals (SURVEY.md §8b "inputs") */
+static void sync_topology(void)
+{
+   int in, n, c, i, j, d, na = sorted_index[num_refine+1];
+   mamr_block *tb;
+   mamr_comm_dir dirs[3];
+   if (!topo_dirty) return;
+   tb = (mamr_block *) malloc((size_t)(na > 0 ? na : 1)*sizeof(mamr_block));
+   for (in = 0; in < na; in++) {
+      block *bp = &blocks[n = sorted_list[in].n];
+      tb[in].slot = n;
+      tb[in].level = bp->level;
+      for (c = 0; c < 6; c++) {
+         tb[in].nei_level[c] = bp->nei_level[c];
+         for (i = 0; i < 2; i++)
+            for (j = 0; j < 2; j++)
+               /* entries the reference never reads are left as they are, except
+                  that only [0][0] is meaningful unless the neighbour is finer */
+               tb[in].nei[c][i][j] = (bp->nei_level[c] == bp->level + 1) ? bp->nei[c][i][j]
+                                                                          : bp->nei[c][0][0];
+      }
+   }
+   OK(mamr_set_topology(G, na, tb), "set_topology");
+   free(tb);
+   for (d = 0; d < 3; d++) {
+      dirs[d].num_partners = num_comm_partners[d];
+      dirs[d].partner = comm_partner[d];
+      dirs[d].index = comm_index[d];
+      dirs[d].num = comm_num[d];
+      dirs[d].send_size = send_size[d];
+      dirs[d].recv_size = recv_size[d];
+      dirs[d].num_cases = num_cases[d];
+      dirs[d].block = comm_block[d];
+      dirs[d].face_case = comm_face_case[d];
+      dirs[d].send_off = comm_send_off[d];
+      dirs[d].recv_off = comm_recv_off[d];
+   }
+   OK(mamr_set_comm_lists(G, dirs), "set_comm_lists");
+   topo_dirty = 0;
+}
+
+static void ready(void)
+{
+   ensure_ctx();
+   upload_host_blocks();
+   sync_topology();
+}
+
+/* feed the profile globals (profile.c reads them): SURVEY.md §5 */
+static void pull_counters(void)
+{
+   mamr_counters c;
+   int d;
+   OK(mamr_get_counters(G, &c), "get_counters");
+   for (d = 0; d < 3; d++) {
+      counter_same[d] += (int)(c.counter_same[d] - seen.counter_same[d]);
+      counter_diff[d] += (int)(c.counter_diff[d] - seen.counter_diff[d]);
+      counter_bc[d] += (int)(c.counter_bc[d] - seen.counter_bc[d]);
+      counter_halo_send[d] += (int)(c.counter_halo_send[d] - seen.counter_halo_send[d]);
+      counter_halo_recv[d] += (int)(c.counter_halo_recv[d] - seen.counter_halo_recv[d]);
+      counter_face_send[d] += (int)(c.counter_face_send[d] - seen.counter_face_send[d]);
+      counter_face_recv[d] += (int)(c.counter_face_recv[d] - seen.counter_face_recv[d]);
+      size_mesg_send[d] += c.size_mesg_send[d] - seen.size_mesg_send[d];
+      size_mesg_recv[d] += c.size_mesg_recv[d] - seen.size_mesg_recv[d];
+   }
+   total_fp_adds += c.total_fp_adds - seen.total_fp_adds;
+   total_fp_divs += c.total_fp_divs - seen.total_fp_divs;
+   seen = c;
+}
+
+static int sync_timers(void)
+{
+   static int v = -1;
+   if (v < 0) v = getenv("MAMR_SYNC_TIMERS") ? atoi(getenv("MAMR_SYNC_TIMERS")) : 0;
+   return v;
+}
+
+/* ---- the reference's call surface (proto.h) -------------------------------- */
+
+void comm(int start, int num_comm, int stage)
+{
+   double t1 = timer();
+   int d;
+   ready();
+   OK(mamr_comm(G, start, num_comm, stage), "comm");
+   pull_counters();
+   if (sync_timers()) OK(mamr_sync(G), "sync");
+   /* the three phases run as one device pass: the reference's per-direction
+      timers get an equal share */
+   t1 = (timer() - t1)/3.0;
+   for (d = 0; d < 3; d++) timer_comm_dir[d] += t1;
+}
+
+void stencil_driver(int var, int calc_stage)
+{
+   ready();
+   OK(mamr_stencil_driver(G, var, calc_stage), "stencil_driver");
+   pull_counters();
+   if (sync_timers() && var == num_vars - 1) OK(mamr_sync(G), "sync");
+}
+
+/* north_star's alias (F1 of SURVEY.md: file-local in the reference) */
+void stencil_calc(int var) { stencil_driver(var, 0); }
+
+double check_sum(int var)
+{
+   double t1 = timer(), sum = 0.0;
+   ready();
+   OK(mamr_check_sum(G, var, &sum), "check_sum");
+   timer_cs_calc += timer() - t1;     /* reduction included: one device pass */
+   total_red++;
+   return sum;
+}
+
+/* pack_block/unpack_block: 50 int slots of header exactly as the receiver's
+ * unpack expects them (pack.c:43-65), then the interiors var-major from the
+ * device (pack.c:66-70).  The message still travels through send_buff/recv_buff
+ * and the host MPI of rcb.c:207-337. */
+static int *hdr_fields(block *bp, int *h, int unpack)
+{
+   int i, j, k, *f[5];
+   f[0] = &bp->level; f[1] = &bp->refine; f[2] = &bp->b_type; f[3] = &bp->parent_node;
+   f[4] = &bp->child_number;
+   for (i = 0; i < 5; i++, h++) if (unpack) *f[i] = *h; else *h = *f[i];
+   for (i = 0; i < 6; i++) {
+      if (unpack) { bp->nei_refine[i] = h[0]; bp->nei_level[i] = h[1]; }
+      else { h[0] = bp->nei_refine[i]; h[1] = bp->nei_level[i]; }
+      h += 2;
+      for (j = 0; j < 2; j++)
+         for (k = 0; k < 2; k++, h++)
+            if (unpack) bp->nei[i][j][k] = *h; else *h = bp->nei[i][j][k];
+   }
+   for (i = 0; i < 3; i++, h++) if (unpack) bp->cen[i] = *h; else *h = bp->cen[i];
+   return h;
+}
+
+void pack_block(int n)
+{
+   block *bp = &blocks[n];
+   long long *ll = (long long *) send_buff;
+   int *end;
+   ready();
+   ll[0] = (long long) bp->number;
+   ll[1] = (bp->parent_node == my_pe && bp->parent != -1) ? (long long)(-2 - bp->parent)
+                                                          : (long long) bp->parent;
+   ll[2] = (long long) bp->num_prime;
+   end = hdr_fields(bp, (int *) send_buff + 6, 0);
+   /* the payload starts at double index (number of int slots used): pack.c:66 */
+   OK(mamr_pack_block(G, n, send_buff + (end - (int *) send_buff)), "pack_block");
+}
+
+void unpack_block(int n)
+{
+   block *bp = &blocks[n];
+   long long *ll = (long long *) recv_buff;
+   int *end;
+   ready();
+   bp->new_proc = -1;
+   bp->number = (num_sz) ll[0];
+   bp->parent = (num_sz) ll[1];
+   bp->num_prime = (num_sz) ll[2];
+   end = hdr_fields(bp, (int *) recv_buff + 6, 1);
+   OK(mamr_unpack_block(G, n, recv_buff + (end - (int *) recv_buff)), "unpack_block");
+   topo_dirty = 1;
+}
+
+/* ---- link-time interception of the in-line array loops --------------------- */
+
+void __real_init(void);
+void __wrap_init(void)
+{
+   host_fresh = 1;       /* init.c:484-495 writes blocks[].array; init.c:682 then calls
+                            check_sum(), which uploads */
+   topo_dirty = 1;
+   __real_init();
+   topo_dirty = 1;
+}
+
+void __real_refine(int ts);
+void __wrap_refine(int ts)
+{
+   __real_refine(ts);
+   topo_dirty = 1;
+}
+
+typedef struct { num_sz number; int level, slot, idx; int child[8]; } famrec;
+
+static int cmp_split(const void *a, const void *b)
+{
+   const famrec *x = (const famrec *) a, *y = (const famrec *) b;
+   if (x->level != y->level) return x->level - y->level;     /* block.c:60: by level, */
+   return x->slot - y->slot;                                   /* :62: then by slot     */
+}
+
+static int cmp_cons(const void *a, const void *b)
+{
+   const famrec *x = (const famrec *) a, *y = (const famrec *) b;
+   if (x->level != y->level) return y->level - x->level;     /* block.c:365: level down, */
+   return x->idx - y->idx;                                     /* :366: parent index up    */
+}
+
+void __real_split_blocks(void);
+void __wrap_split_blocks(void)
+{
+   /* who is about to be split, and where it lives now */
+   int n, p, o, nrec = 0, k;
+   famrec *rec;
+   ready();
+   rec = (famrec *) malloc((size_t)(max_active_block > 0 ? max_active_block : 1)*sizeof(famrec));
+   for (n = 0; n < max_active_block; n++)
+      if (blocks[n].number >= 0 && blocks[n].refine == 1) {
+         rec[nrec].number = blocks[n].number;
+         rec[nrec].level = blocks[n].level;
+         rec[nrec].slot = n;
+         rec[nrec].idx = -1;
+         nrec++;
+      }
+   __real_split_blocks();          /* topology, comm lists, sorted list: unchanged host code */
+   /* find the parent entry each of them became: same number and level */
+   for (k = 0; k < nrec; k++)
+      for (p = 0; p < max_active_parent; p++)
+         if (parents[p].number == rec[k].number && parents[p].level == rec[k].level) {
+            rec[k].idx = p;
+            for (o = 0; o < 8; o++) rec[k].child[o] = (int) parents[p].child[o];
+            break;
+         }
+   /* replay the data copies in the reference's own order: a freed parent slot
+      may be a later family's child slot, never an earlier one's */
+   qsort(rec, nrec, sizeof(famrec), cmp_split);
+   for (k = 0; k < nrec; k++) {
+      if (rec[k].idx < 0) continue;           /* not split after all */
+      OK(mamr_split_block(G, rec[k].slot, rec[k].child), "split_block");
+   }
+   free(rec);
+   topo_dirty = 1;
+}
+
+void __real_consolidate_blocks(void);
+void __wrap_consolidate_blocks(void)
+{
+   int n, p, o, nrec = 0, k;
+   famrec *rec;
+   ready();
+   rec = (famrec *) malloc((size_t)(max_active_parent > 0 ? max_active_parent : 1)*sizeof(famrec));
+   for (p = 0; p < max_active_parent; p++)
+      if (parents[p].number >= 0 && parents[p].refine == -1) {
+         rec[nrec].number = parents[p].number;
+         rec[nrec].level = parents[p].level;
+         rec[nrec].idx = p;
+         rec[nrec].slot = -1;
+         nrec++;
+      }
+   __real_consolidate_blocks();
+   for (k = 0; k < nrec; k++) {
+      /* child[] is read AFTER the host pass: a child that was itself re-formed in
+         this call (one level further down) now names its new block (block.c:393) */
+      for (o = 0; o < 8; o++) rec[k].child[o] = (int) parents[rec[k].idx].child[o];
+      for (n = 0; n < max_active_block; n++)
+         if (blocks[n].number == rec[k].number && blocks[n].level == rec[k].level) {
+            rec[k].slot = n;
+            break;
+         }
+   }
+   qsort(rec, nrec, sizeof(famrec), cmp_cons);
+   for (k = 0; k < nrec; k++) {
+      if (rec[k].slot < 0) continue;
+      OK(mamr_consolidate_block(G, rec[k].child, rec[k].slot), "consolidate_block");
+   }
+   free(rec);
+   topo_dirty = 1;
+}

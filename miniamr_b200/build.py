@@ -40,7 +40,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         return LIB
     cmd = [nvcc_path(), "-O3", "-std=c++17",
            "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-           "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-o", LIB] + SRCS + ["-ldl"]
+           "-Xcompiler", "-fPIC,-O3,-Wall", "-shared",
+           "-Xlinker", "-soname=libminiamr_b200.so", "-o", LIB] + SRCS + ["-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     env = dict(os.environ)

@@ -1010,6 +1010,25 @@ int mamr_set_topology(mamr_ctx *c, int num_active, const mamr_block *sorted_bloc
    for (int a = 0; a < num_active; a++)
       if (sorted_blocks[a].slot < 0 || sorted_blocks[a].slot >= c->p.max_blocks)
          return fail(MAMR_EINVAL, "active block %d has slot %d out of range", a, sorted_blocks[a].slot);
+   // A slot that just became inactive keeps its last content in the reference
+   // (a later split_blocks()/unpack_block() only rewrites the interior, so the
+   // ghost cells of the new block are whatever the slot held).  Make both pools
+   // agree on it now: later pool flips then cannot change what a reused slot holds.
+   {
+      std::vector<char> now(c->p.max_blocks, 0);
+      for (int a = 0; a < num_active; a++) now[sorted_blocks[a].slot] = 1;
+      const Geometry &g = c->g;
+      for (const mamr_block &b : c->blocks)
+         if (!now[b.slot])
+            for (const Run &r : runs_of(c, 0, c->p.num_vars, false))
+               CU(cudaMemcpy2DAsync(c->pool[c->cur[r.start] ^ 1] + (long long)r.start*g.var_stride +
+                                       tile_base(g, b.slot),
+                                    g.var_stride*sizeof(double),
+                                    vpool(c, r.start) + (long long)r.start*g.var_stride +
+                                       tile_base(g, b.slot),
+                                    g.var_stride*sizeof(double), g.tile*sizeof(double), r.num,
+                                    cudaMemcpyDeviceToDevice, c->stream));
+   }
    c->blocks.assign(sorted_blocks, sorted_blocks + num_active);
    c->num_active = num_active;
    if ((size_t)num_active > c->slots_cap) {

@@ -150,6 +150,15 @@ long long refh_get_parent(int p, int *out)
    return (long long) pp->number;
 }
 
+/* integration build only (integration/glue.c): bring the device-resident block
+ * data back into blocks[].array before the getters below read it */
+void mamr_glue_sync_host(void) __attribute__((weak));
+void refh_sync_host(void)
+{
+   if (mamr_glue_sync_host)
+      mamr_glue_sync_host();
+}
+
 /* flatten one (slot, var) tile, k fastest, ghosts included */
 void refh_get_tile(int slot, int var, double *out)
 {
@@ -228,11 +237,14 @@ void refh_get_counters(int *out)
 double refh_get_grid_sum(int var) { return grid_sum[var]; }
 long long refh_global_active(void) { return (long long) global_active; }
 
-/* comm.c:245 / 993 — public in proto.h:50-51, never reached at one rank */
+/* comm.c:245 / 993 — public in proto.h:50-51, never reached at one rank.
+ * (weak: the integration build replaces comm.c and has no such symbols) */
+#pragma weak pack_face
+#pragma weak unpack_face
 void refh_pack_face(double *buf, int slot, int face_case, int dir, int start, int num_comm)
-{ pack_face(buf, slot, face_case, dir, start, num_comm); }
+{ if (pack_face) pack_face(buf, slot, face_case, dir, start, num_comm); }
 void refh_unpack_face(double *buf, int slot, int face_case, int dir, int start, int num_comm)
-{ unpack_face(buf, slot, face_case, dir, start, num_comm); }
+{ if (unpack_face) unpack_face(buf, slot, face_case, dir, start, num_comm); }
 
 /* glibc rand() state is process-wide; reseed to the default (1) so that every
  * instance reproduces the reference's never-seeded sequence (init.c:490-494) */

@@ -20,6 +20,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
+INT_DIR = os.path.join(os.path.dirname(HERE), "integration", "_bin")
 
 P_NAMES = ["nx", "ny", "nz", "num_vars", "comm_vars", "max_blocks", "stencil",
            "num_refine", "num_active", "max_active_block", "code", "permute",
@@ -28,8 +29,16 @@ P_NAMES = ["nx", "ny", "nz", "num_vars", "comm_vars", "max_blocks", "stencil",
            "error_tol"]
 
 
+def lib_path(variant: str) -> str:
+    """"ref" / "omp": the unmodified reference; "int": the same host code linked
+    against the CUDA stage path through integration/glue.c."""
+    if variant == "int":
+        return os.path.join(INT_DIR, "libminiamr_int.so")
+    return os.path.join(REF_DIR, f"libminiamr_{variant}.so")
+
+
 def available(variant: str = "ref") -> bool:
-    return os.path.exists(os.path.join(REF_DIR, f"libminiamr_{variant}.so"))
+    return os.path.exists(lib_path(variant))
 
 
 class RefMiniAMR:
@@ -37,9 +46,14 @@ class RefMiniAMR:
 
     def __init__(self, args, variant: str = "ref", run_driver: bool = False,
                  quiet: bool = True):
-        src = os.path.join(REF_DIR, f"libminiamr_{variant}.so")
+        src = lib_path(variant)
         if not os.path.exists(src):
-            raise FileNotFoundError(f"{src} missing: run `make -C oracle`")
+            raise FileNotFoundError(f"{src} missing: run `make -C oracle` / `make -C integration`")
+        if variant == "int":
+            # the private copy below cannot use its $ORIGIN-relative rpath: make the
+            # CUDA library resident first, the copy then binds to it by soname
+            C.CDLL(os.path.join(os.path.dirname(HERE), "miniamr_b200", "libminiamr_b200.so"),
+                   mode=C.RTLD_GLOBAL)
         fd, self._copy = tempfile.mkstemp(suffix=".so", prefix="miniamr_ref_")
         os.close(fd)
         shutil.copyfile(src, self._copy)
@@ -61,6 +75,7 @@ class RefMiniAMR:
         for i, a in enumerate(argv):
             arr[i] = a.encode()
         self._argv = arr
+        L.refh_reseed()   # rand() state is process-wide; every instance starts at seed 1
         L.refh_start(len(argv), arr, 1 if run_driver else 0)
         self.refresh()
 
@@ -141,6 +156,10 @@ class RefMiniAMR:
         d = np.ascontiguousarray(data, dtype=np.float64).reshape(-1)
         assert d.size == self.tile * self.p["num_vars"]
         self.lib.refh_set_slot(int(slot), d.ctypes.data_as(C.c_void_p))
+
+    def sync_host(self):
+        """integration build: copy the device-resident block data back to blocks[].array"""
+        self.lib.refh_sync_host()
 
     def get_active(self) -> dict:
         """{slot: array[num_vars, nx+2, ny+2, nz+2]} for every active block."""

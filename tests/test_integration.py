@@ -1,0 +1,93 @@
+"""The drop-in: the UNMODIFIED reference host code (driver.c, refine.c, block.c, ...)
+linked against the CUDA stage path through integration/glue.c, run side by side
+with the unmodified reference on the same command line.  Whole runs — initial
+refinement, moving object, split/consolidate, checksums every few stages —
+must end in bit-identical block data (ghost cells included) and the same mesh."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import refharness
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+needs_libs = pytest.mark.skipif(not (refharness.available("ref") and refharness.available("int")),
+                                reason="oracle/_ref or integration/_bin not built")
+
+MOVING = "--num_objects 1 --object 2 0 0.2 0.2 0.2 0.09 0.07 0.05 0.2 0.2 0.2 0 0 0"
+SPHERE = "--num_objects 1 --object 2 0 0.3 0.3 0.3 0.01 0.01 0.01 0.25 0.25 0.25 0 0 0"
+RUNS = {
+    "amr7_moving": f"--nx 4 --ny 4 --nz 4 --num_vars 4 --comm_vars 3 --num_refine 3 --block_change 1 "
+                   f"--max_blocks 3000 --refine_freq 1 --num_tsteps 6 --stages_per_ts 4 --checksum_freq 2 {MOVING}",
+    "amr7_cfg1_shape": f"--nx 10 --ny 10 --nz 10 --num_vars 3 --num_refine 3 --max_blocks 2000 "
+                       f"--num_tsteps 3 --stages_per_ts 5 --refine_freq 1 {SPHERE}",
+    "uni27": "--nx 4 --ny 6 --nz 4 --num_vars 3 --stencil 27 --uniform_refine 1 --num_refine 1 "
+             "--init_x 2 --init_y 1 --init_z 2 --max_blocks 100 --num_tsteps 2 --stages_per_ts 5",
+    "amr7_permute": f"--nx 6 --ny 4 --nz 8 --num_vars 2 --num_refine 2 --max_blocks 1000 --permute "
+                    f"--refine_freq 2 --num_tsteps 4 --stages_per_ts 7 {MOVING}",
+}
+
+
+@needs_libs
+@pytest.mark.parametrize("name", sorted(RUNS))
+def test_whole_run_matches_reference(name):
+    args = RUNS[name].split()
+    ref = refharness.RefMiniAMR(args, variant="ref", run_driver=True)
+    dev = refharness.RefMiniAMR(args, variant="int", run_driver=True)
+    assert ref.p == dev.p
+    rs, rl, rnl, rne = ref.topology()
+    ds, dl, dnl, dne = dev.topology()
+    assert (rs == ds).all() and (rl == dl).all() and (rnl == dnl).all()
+    assert len(rs) > 8
+    # the run ends with refine(): blocks created there have had no exchange yet and
+    # their ghosts are whatever the slot held.  One more comm() defines every face.
+    ref.comm(0, ref.p["num_vars"], 0)
+    dev.comm(0, dev.p["num_vars"], 0)
+    dev.sync_host()
+    # cells the 7-point exchange never writes (ghost edges and corners) hold whatever
+    # malloc() gave the reference (main.c:446 does not clear; split_blocks() only
+    # writes child interiors): indeterminate there, so not compared
+    nx, ny, nz = ref.p["nx"], ref.p["ny"], ref.p["nz"]
+    defined = np.ones((nx + 2, ny + 2, nz + 2), bool)
+    if ref.p["stencil"] == 7:
+        gi = np.zeros(nx + 2, int); gi[[0, -1]] = 1
+        gj = np.zeros(ny + 2, int); gj[[0, -1]] = 1
+        gk = np.zeros(nz + 2, int); gk[[0, -1]] = 1
+        defined = (gi[:, None, None] + gj[None, :, None] + gk[None, None, :]) <= 1
+    for s in rs:
+        a, b = ref.get_slot(int(s)), dev.get_slot(int(s))
+        bad = (a.view(np.uint64) != b.view(np.uint64)) & defined[None]
+        assert not bad.any(), f"{name}: slot {s}: {int(bad.sum())} cells differ, first {np.argwhere(bad)[0]}"
+    for v in range(ref.p["num_vars"]):
+        r, d = ref.lib.refh_get_grid_sum(v), dev.lib.refh_get_grid_sum(v)
+        assert abs(r - d) <= 1e-13*abs(r)
+    rc, dc = ref.counters(), dev.counters()
+    assert rc == dc                       # same/diff/bc face counters feed profile.c
+    assert ref.timers()["fp_adds"] == dev.timers()["fp_adds"]
+
+
+@needs_libs
+def test_executable_prints_the_reference_checksums():
+    """miniAMR_b200.x is the reference's own main(): same flags, same report."""
+    args = (f"--nx 6 --ny 6 --nz 6 --num_vars 3 --num_refine 2 --max_blocks 500 --num_tsteps 3 "
+            f"--stages_per_ts 4 --checksum_freq 1 --report_diffusion --report_perf 4 {SPHERE}").split()
+    outs = []
+    for exe in (os.path.join(ROOT, "oracle", "_ref", "miniAMR_ref.x"),
+                os.path.join(ROOT, "integration", "_bin", "miniAMR_b200.x")):
+        r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        outs.append(r.stdout)
+    pat = re.compile(r"^\d+ var \d+ sum ")        # driver.c:93-95
+    ref_lines = [l for l in outs[0].splitlines() if pat.match(l)]
+    dev_lines = [l for l in outs[1].splitlines() if pat.match(l)]
+    assert len(ref_lines) >= 3*4*3 and len(ref_lines) == len(dev_lines)
+    nums = lambda l: [float(x) for x in re.findall(r"-?\d+\.\d+(?:[eE][-+]?\d+)?", l)]
+    for a, b in zip(ref_lines, dev_lines):
+        na, nb = nums(a), nums(b)
+        assert len(na) == len(nb) and len(na) >= 2
+        # sums to the printed precision; the tiny stage-to-stage differences only roughly
+        assert abs(na[0] - nb[0]) <= 2e-6 and abs(na[1] - nb[1]) <= 2e-6, (a, b)
+    assert "difference too large" not in outs[1]

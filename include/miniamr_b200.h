@@ -163,6 +163,27 @@ int mamr_nccl_get_unique_id(char id[MAMR_NCCL_ID_BYTES]);   /* rank 0, then broa
                                                                over the host channel */
 int mamr_nccl_init(mamr_ctx *ctx, const char id[MAMR_NCCL_ID_BYTES]);
 
+/* ---- host-only view of the halo plan (no device needed; tests and tools) --
+ * The plan is what the fused stage kernel executes for one comm() call: for
+ * every ghost region of every active block the place its value comes from once
+ * the three direction phases of comm.c:42-242 are done, and, per phase, the ops
+ * that fill the send buffers (pack_face, comm.c:254-401).  An op is 19 values:
+ *   dst_base src_base dst_vs src_vs ext[3] dst_str[3] src_str[3] S F first mode
+ *   dst_mem src_mem
+ * (csrc/common.cuh BoxOp; mode 0 copy, 1 /4, 2 prolong /4, 3 replicate, 4 4-term
+ * sum; mem 0 = block pool / the block's own tile, 1+d = message buffer of
+ * direction d).  which = 0: halo ops (CSR by active block via
+ * mamr_plan_block_begin), 1..3: pack ops of phase which-1. */
+#define MAMR_PLAN_OP_FIELDS 19
+typedef struct mamr_plan mamr_plan;
+int  mamr_plan_create(const mamr_params *params, int num_active, const mamr_block *sorted_blocks,
+                      const mamr_comm_dir dirs[3], int stage, mamr_plan **out);
+int  mamr_plan_phase_dir(mamr_plan *plan, int phase);          /* direction of phase 0..2 */
+int  mamr_plan_num_ops(mamr_plan *plan, int which);
+int  mamr_plan_get_ops(mamr_plan *plan, int which, long long *fields);
+int  mamr_plan_block_begin(mamr_plan *plan, int *begin);       /* num_active + 1 entries */
+void mamr_plan_destroy(mamr_plan *plan);
+
 /* ---- measurement helpers (bench.py) ------------------------------------- */
 /* CUDA-event timing on the library's own stream: mark begin/end around any
  * sequence of calls; elapsed in milliseconds. */

@@ -64,6 +64,8 @@ EXPORTS = [
     "mamr_consolidate_block", "mamr_pack_block", "mamr_unpack_block", "mamr_send_block",
     "mamr_recv_block", "mamr_nccl_get_unique_id", "mamr_nccl_init", "mamr_timer_begin",
     "mamr_timer_end", "mamr_kernel_timing", "mamr_kernel_time_ms",
+    "mamr_plan_create", "mamr_plan_phase_dir", "mamr_plan_num_ops", "mamr_plan_get_ops",
+    "mamr_plan_block_begin", "mamr_plan_destroy",
 ]
 
 _LIB = None
@@ -99,6 +101,70 @@ def _dp(a):
 
 def _ip(a):
     return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _block_array(slots, level, nei_level, nei):
+    n = len(slots)
+    arr = (Block * max(n, 1))()
+    packed = np.zeros((max(n, 1), 32), np.int32)
+    if n:
+        packed[:n, 0] = slots
+        packed[:n, 1] = level
+        packed[:n, 2:8] = np.asarray(nei_level, np.int32).reshape(n, 6)
+        packed[:n, 8:32] = np.asarray(nei, np.int32).reshape(n, 24)
+    C.memmove(arr, packed.ctypes.data, packed.nbytes)
+    return arr
+
+
+def _comm_dirs(dirs):
+    arr = (CommDir * 3)()
+    keep = []
+    for d in range(3):
+        D = dirs[d] if dirs else {}
+        a = {k: np.ascontiguousarray(D.get(k, []), np.int32) for k in
+             ("partner", "index", "num", "send_size", "recv_size", "block", "face_case",
+              "send_off", "recv_off")}
+        keep.append(a)
+        arr[d].num_partners = len(a["partner"])
+        arr[d].num_cases = len(a["block"])
+        for k in a:
+            setattr(arr[d], k, _ip(a[k]))
+    return arr, keep
+
+
+PLAN_FIELDS = ("dst_base src_base dst_vs src_vs e0 e1 e2 ds0 ds1 ds2 ss0 ss1 ss2 S F first mode "
+               "dst_mem src_mem").split()
+
+
+class HaloPlan:
+    """Host-only view of what one comm() call resolves to (no device needed):
+    .halo  int64[n_ops, 19] + .begin int32[num_active+1]; .pack[o] per phase;
+    .dirs[o] the direction of phase o.  Field names in PLAN_FIELDS."""
+
+    def __init__(self, nx, ny, nz, num_vars, max_blocks, slots, level, nei_level, nei, dirs=None,
+                 stencil=7, comm_vars=0, permute=0, stage=0, rank=0, num_ranks=1):
+        L = load_library()
+        prm = Params(nx, ny, nz, num_vars, comm_vars, max_blocks, stencil, 0, permute, -1, rank,
+                     num_ranks)
+        blocks = _block_array(slots, level, nei_level, nei)
+        darr, keep = _comm_dirs(dirs)
+        h = C.c_void_p()
+        if L.mamr_plan_create(C.byref(prm), len(slots), blocks, darr, int(stage), C.byref(h)):
+            raise MamrError(L.mamr_last_error().decode())
+        try:
+            def ops(which):
+                n = L.mamr_plan_num_ops(h, which)
+                out = np.zeros((max(n, 0), len(PLAN_FIELDS)), np.int64)
+                if n > 0 and L.mamr_plan_get_ops(h, which, _dp(out)):
+                    raise MamrError(L.mamr_last_error().decode())
+                return out
+            self.halo = ops(0)
+            self.pack = [ops(1), ops(2), ops(3)]
+            self.begin = np.zeros(len(slots) + 1, np.int32)
+            L.mamr_plan_block_begin(h, _ip(self.begin))
+            self.dirs = [L.mamr_plan_phase_dir(h, o) for o in range(3)]
+        finally:
+            L.mamr_plan_destroy(h)
 
 
 class DeviceMesh:

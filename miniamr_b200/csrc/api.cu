@@ -1387,6 +1387,104 @@ int mamr_nccl_init(mamr_ctx *c, const char id[MAMR_NCCL_ID_BYTES])
    return MAMR_OK;
 }
 
+// ---- host-only plan view ---------------------------------------------------
+struct mamr_plan {
+   HaloPlan halo;
+   std::vector<BoxOp> pack[3];
+   int order[3];
+};
+
+int mamr_plan_create(const mamr_params *params, int num_active, const mamr_block *sorted_blocks,
+                     const mamr_comm_dir dirs[3], int stage, mamr_plan **out)
+{
+   if (!params || !out || num_active < 0 || (num_active && !sorted_blocks))
+      return fail(MAMR_EINVAL, "null argument");
+   const mamr_params &p = *params;
+   if (p.nx <= 0 || p.ny <= 0 || p.nz <= 0 || ((p.nx | p.ny | p.nz) & 1) || p.max_blocks <= 0)
+      return fail(MAMR_EINVAL, "bad geometry");
+   Geometry g;
+   g.n[0] = p.nx; g.n[1] = p.ny; g.n[2] = p.nz;
+   g.str[2] = 1; g.str[1] = p.nz + 2; g.str[0] = (p.ny + 2)*(p.nz + 2);
+   g.tile = (p.nx + 2)*g.str[0];
+   g.tile_stride = ((long long)g.tile + 15)/16*16;
+   g.var_stride = g.tile_stride*p.max_blocks;
+   std::vector<mamr_block> blocks(sorted_blocks, sorted_blocks + num_active);
+   for (const mamr_block &b : blocks)
+      if (b.slot < 0 || b.slot >= p.max_blocks) return fail(MAMR_EINVAL, "slot out of range");
+   DirLists cl[3];
+   bool partners = false;
+   for (int d = 0; d < 3 && dirs; d++) {
+      const mamr_comm_dir &s = dirs[d];
+      DirLists &L = cl[d];
+      L.partner.assign(s.partner, s.partner + s.num_partners);
+      L.index.assign(s.index, s.index + s.num_partners);
+      L.num.assign(s.num, s.num + s.num_partners);
+      L.send_size.assign(s.send_size, s.send_size + s.num_partners);
+      L.recv_size.assign(s.recv_size, s.recv_size + s.num_partners);
+      L.block.assign(s.block, s.block + s.num_cases);
+      L.face_case.assign(s.face_case, s.face_case + s.num_cases);
+      L.send_off.assign(s.send_off, s.send_off + s.num_cases);
+      L.recv_off.assign(s.recv_off, s.recv_off + s.num_cases);
+      if (s.num_partners) partners = true;
+   }
+   mamr_plan *P = new mamr_plan();
+   const int ord = p.permute ? ((stage%6) + 6)%6 : 0;
+   PlanInput in;
+   in.g = &g; in.stencil = p.stencil; in.max_blocks = p.max_blocks; in.blocks = &blocks; in.cl = cl;
+   for (int o = 0; o < 3; o++) in.order[o] = P->order[o] = kPerm[ord][o];
+   build_halo_plan(in, P->halo);
+   std::string why = P->halo.why;
+   bool ok = P->halo.ok;
+   for (int o = 0; o < 3 && ok && partners; o++) ok = build_pack_plan(in, o, P->pack[o], why);
+   if (!ok) {
+      delete P;
+      return fail(why.find("misconnected") != std::string::npos ? MAMR_ETOPOLOGY : MAMR_EUNSUPPORTED,
+                  "%s", why.c_str());
+   }
+   *out = P;
+   return MAMR_OK;
+}
+
+int mamr_plan_phase_dir(mamr_plan *P, int phase)
+{
+   return (P && phase >= 0 && phase < 3) ? P->order[phase] : -1;
+}
+
+static const std::vector<BoxOp> *plan_ops(mamr_plan *P, int which)
+{
+   if (!P || which < 0 || which > 3) return nullptr;
+   return which == 0 ? &P->halo.ops : &P->pack[which - 1];
+}
+
+int mamr_plan_num_ops(mamr_plan *P, int which)
+{
+   const std::vector<BoxOp> *v = plan_ops(P, which);
+   return v ? (int)v->size() : -1;
+}
+
+int mamr_plan_get_ops(mamr_plan *P, int which, long long *f)
+{
+   const std::vector<BoxOp> *v = plan_ops(P, which);
+   if (!v || !f) return fail(MAMR_EINVAL, "bad plan query");
+   for (const BoxOp &o : *v) {
+      *f++ = o.dst_base; *f++ = o.src_base; *f++ = o.dst_vs; *f++ = o.src_vs;
+      for (int a = 0; a < 3; a++) *f++ = o.ext[a];
+      for (int a = 0; a < 3; a++) *f++ = o.dst_str[a];
+      for (int a = 0; a < 3; a++) *f++ = o.src_str[a];
+      *f++ = o.S; *f++ = o.F; *f++ = o.first; *f++ = o.mode; *f++ = o.dst_mem; *f++ = o.src_mem;
+   }
+   return MAMR_OK;
+}
+
+int mamr_plan_block_begin(mamr_plan *P, int *begin)
+{
+   if (!P || !begin) return fail(MAMR_EINVAL, "bad plan query");
+   for (size_t i = 0; i < P->halo.begin.size(); i++) begin[i] = P->halo.begin[i];
+   return MAMR_OK;
+}
+
+void mamr_plan_destroy(mamr_plan *P) { delete P; }
+
 // ---- measurement -----------------------------------------------------------
 int mamr_timer_begin(mamr_ctx *c)
 {

@@ -86,6 +86,9 @@ typedef struct {
    long long total_red;                                         /* check_sum.c:62         */
    long long kernel_launches;                                   /* CUDA kernels launched  */
    double migrate_bytes;                                        /* block payload bytes moved */
+   long long ghost_regens;                                      /* ghost layers an eliding stage
+                                                                   left stale and that had to be
+                                                                   regenerated on demand */
 } mamr_counters;
 
 enum { MAMR_OK = 0, MAMR_ECUDA = 1, MAMR_EINVAL = 2, MAMR_EUNSUPPORTED = 3,

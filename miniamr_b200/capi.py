@@ -51,7 +51,7 @@ class Counters(C.Structure):
                 ("size_mesg_send", C.c_double * 3), ("size_mesg_recv", C.c_double * 3),
                 ("total_fp_adds", C.c_double), ("total_fp_divs", C.c_double),
                 ("total_red", C.c_longlong), ("kernel_launches", C.c_longlong),
-                ("migrate_bytes", C.c_double)]
+                ("migrate_bytes", C.c_double), ("ghost_regens", C.c_longlong)]
 
 
 EXPORTS = [

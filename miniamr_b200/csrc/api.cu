@@ -112,6 +112,27 @@ struct mamr_ctx {
    std::vector<int> pc_start;
    bool fused_geom = false;     // the tile fits the fused kernel
    bool use_fused = true;       // MAMR_NO_FUSED=1 forces the split path
+   bool fused2_geom = false;    // fused2.cu has an instantiation for this block size
+   bool use_fused2 = true;      // MAMR_NO_FUSED2=1: always the generic fused kernel
+   bool use_elide = true;       // MAMR_NO_ELIDE=1: fused2 always stores whole tiles
+   // Ghost elision.  After an eliding fused2 launch the i-ghost planes and j-ghost
+   // rows of variable v's current tiles are stale; they equal the halo plan
+   // `stale_ord[v]` applied to the OTHER pool (the state that launch read) and the
+   // receive buffers of the comm() that started at variable stale_start[v].
+   std::vector<char> stale;
+   std::vector<signed char> stale_ord;
+   std::vector<int> stale_start;
+   // both pools agree on the ghost regions no phase ever writes (BF_IDENT)
+   std::vector<char> shell_synced;
+   // Z-face exports, one pool per tile pool (fused2.cu): zf[p][var][slot][side][nx*ny];
+   // zf_ok[v]: the export pool of v's current pool matches its tiles
+   double *zf[2] = {nullptr, nullptr};
+   size_t zf_bytes = 0;
+   std::vector<char> zf_ok;
+   long long *d_zsrc[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+   BoxOp *d_lops[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // lean op lists
+   int *d_lbegin[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+   bool plan_has_ident[6] = {false, false, false, false, false, false};
    HaloPlan plan[6];
    std::vector<BoxOp> pack[6][3];       // multi-GPU: send-buffer fill per phase
    BoxOp *d_pack[6][3] = {};
@@ -641,6 +662,62 @@ int ensure_plan(mamr_ctx *c, int ord)
                          cudaMemcpyHostToDevice, c->stream));
    CU(cudaMemcpyAsync(c->d_hbegin[ord], P.begin.data(), P.begin.size()*sizeof(int),
                       cudaMemcpyHostToDevice, c->stream));
+   // eliding launches: identity ops that the stencil does not read are dropped
+   // (7-point: everything but the faces)
+   if (c->d_lops[ord]) CU(cudaFree(c->d_lops[ord]));
+   if (c->d_lbegin[ord]) CU(cudaFree(c->d_lbegin[ord]));
+   c->d_lops[ord] = nullptr;
+   c->d_lbegin[ord] = nullptr;
+   c->plan_has_ident[ord] = false;
+   for (const BoxOp &op : P.ops)
+      if (op.flags & BF_IDENT) c->plan_has_ident[ord] = true;
+   if (c->d_zsrc[ord]) CU(cudaFree(c->d_zsrc[ord]));
+   c->d_zsrc[ord] = nullptr;
+   if (P.elidable && c->fused2_geom) {
+      std::vector<BoxOp> lean;
+      std::vector<int> lbegin(P.begin.size(), 0);
+      const Geometry &g = c->g;
+      const long long zslot = 2LL*g.n[0]*g.n[1];
+      std::vector<long long> zsrc(2*std::max<size_t>(1, P.begin.size() - 1), -1);
+      for (size_t a = 0; a + 1 < P.begin.size(); a++) {
+         lbegin[a] = (int)lean.size();
+         int first = 0;
+         for (int o = P.begin[a]; o < P.begin[a + 1]; o++) {
+            BoxOp op = P.ops[o];
+            if (c->p.stencil == 7 && !(op.flags & BF_FACE)) continue;
+            // a whole Z halo face that is a plain copy of a tile's k=1 / k=nz interior
+            // plane (same-level neighbour or reflective boundary) arrives as one bulk
+            // copy of that tile's export instead of nx*ny scattered 8-byte cells
+            if (op.mode == FM_COPY && op.src_mem == BM_POOL && !(op.flags & BF_GHOST_SRC) &&
+                op.ext[0] == g.n[0] && op.ext[1] == g.n[1] && op.ext[2] == 1 &&
+                op.src_str[0] == g.str[0] && op.src_str[1] == g.str[1]) {
+               const long long lo = g.str[0] + g.str[1], hi = lo + g.n[2] + 1;
+               const long long m = op.src_base/g.tile_stride, cell = op.src_base%g.tile_stride;
+               if ((op.dst_base == lo || op.dst_base == hi) &&
+                   (cell == lo + 1 || cell == lo + g.n[2])) {
+                  zsrc[2*a + (op.dst_base == hi ? 1 : 0)] =
+                     m*zslot + (cell == lo + 1 ? 0 : (long long)g.n[0]*g.n[1]);
+                  continue;
+               }
+            }
+            op.first = first;
+            first += op.ext[0]*op.ext[1]*op.ext[2];
+            lean.push_back(op);
+         }
+      }
+      lbegin[P.begin.size() - 1] = (int)lean.size();
+      CU(cudaMalloc(&c->d_lops[ord], std::max<size_t>(1, lean.size())*sizeof(BoxOp)));
+      CU(cudaMalloc(&c->d_lbegin[ord], lbegin.size()*sizeof(int)));
+      if (!lean.empty())
+         CU(cudaMemcpyAsync(c->d_lops[ord], lean.data(), lean.size()*sizeof(BoxOp),
+                            cudaMemcpyHostToDevice, c->stream));
+      CU(cudaMemcpyAsync(c->d_lbegin[ord], lbegin.data(), lbegin.size()*sizeof(int),
+                         cudaMemcpyHostToDevice, c->stream));
+      CU(cudaMalloc(&c->d_zsrc[ord], zsrc.size()*sizeof(long long)));
+      CU(cudaMemcpyAsync(c->d_zsrc[ord], zsrc.data(), zsrc.size()*sizeof(long long),
+                         cudaMemcpyHostToDevice, c->stream));
+      CU(cudaStreamSynchronize(c->stream));   // the host vectors go out of scope
+   }
    for (int o = 0; o < 3; o++) {
       if (c->d_pack[ord][o]) CU(cudaFree(c->d_pack[ord][o]));
       c->d_pack[ord][o] = nullptr;
@@ -665,6 +742,35 @@ int fused_ready(mamr_ctx *c, int ord, bool *yes)
    return MAMR_OK;
 }
 
+// Ghost cells an eliding fused launch left unwritten become real: the halo plan
+// of that launch applied to the pool it read (fused2.cu: halo_fill_kernel).
+int regen_ghosts(mamr_ctx *c, int v0, int n)
+{
+   int v = v0;
+   while (v < v0 + n) {
+      if (!c->stale[v]) { v++; continue; }
+      int e = v + 1;
+      while (e < v0 + n && c->stale[e] && c->cur[e] == c->cur[v] && c->stale_ord[e] == c->stale_ord[v] &&
+             c->stale_start[e] == c->stale_start[v])
+         e++;
+      const int ord = c->stale_ord[v], in = c->cur[v] ^ 1;
+      if (!c->plan_built[ord] || !c->plan[ord].ok || !c->d_hops[ord])
+         return fail(MAMR_EINVAL, "internal: halo plan of an elided stage is gone");
+      if (c->num_active > 0) {
+         KTimer t(c, KC_GHOST);
+         const double *recv[3] = { c->d_recv[0], c->d_recv[1], c->d_recv[2] };
+         launch_halo_fill(c->d_hops[ord], c->d_hbegin[ord], c->d_slots, c->num_active, c->pool[in],
+                          c->pool[in ^ 1], c->g, recv, v, e - v, c->stale_start[v], false, c->stream);
+         c->cnt.kernel_launches++;
+         c->cnt.ghost_regens++;
+      }
+      for (int u = v; u < e; u++) c->stale[u] = 0;
+      v = e;
+   }
+   CU(cudaGetLastError());
+   return MAMR_OK;
+}
+
 int flush_pending(mamr_ctx *c)
 {
    if (c->pend_num == 0) return MAMR_OK;
@@ -675,19 +781,63 @@ int flush_pending(mamr_ctx *c)
       const int in = c->cur[r.start];
       if (ord >= 0) {
          // comm() + stencil in one pass: current pool -> other pool
+         const double *recv[3] = { c->d_recv[0], c->d_recv[1], c->d_recv[2] };
+         const bool f2 = c->fused2_geom && c->use_fused2;
+         const bool elide = f2 && c->use_elide && c->plan[ord].elidable && c->d_lops[ord];
+         if (elide && c->plan_has_ident[ord] && c->num_active > 0) {
+            // never-written ghost regions: the output pool must already hold them
+            bool synced = true;
+            for (int v = r.start; v < r.start + r.num; v++) synced = synced && c->shell_synced[v];
+            if (!synced) {
+               KTimer t(c, KC_GHOST);
+               launch_halo_fill(c->d_hops[ord], c->d_hbegin[ord], c->d_slots, c->num_active,
+                                c->pool[in], c->pool[in ^ 1], c->g, recv, r.start, r.num,
+                                c->pc_start[r.start], true, c->stream);
+               c->cnt.kernel_launches++;
+            }
+         }
+         if (elide && c->num_active > 0) {
+            // the input tiles' Z-face exports, where no eliding launch wrote them
+            int v = r.start;
+            while (v < r.start + r.num) {
+               if (c->zf_ok[v]) { v++; continue; }
+               int e = v;
+               while (e < r.start + r.num && !c->zf_ok[e]) e++;
+               KTimer t(c, KC_GHOST);
+               launch_zface_extract(c->pool[in], c->zf[in], c->g, c->d_slots, c->num_active, v,
+                                    e - v, c->stream);
+               c->cnt.kernel_launches++;
+               v = e;
+            }
+         }
          {
             KTimer t(c, KC_STENCIL);
-            const double *recv[3] = { c->d_recv[0], c->d_recv[1], c->d_recv[2] };
-            launch_fused(c->pool[in], c->pool[in ^ 1], c->g, c->d_slots, c->d_order, c->num_active,
-                         c->d_hops[ord], c->d_hbegin[ord], recv, r.start, r.num,
-                         c->pc_start[r.start], c->p.stencil, c->stream);
+            if (f2)
+               launch_fused2(c->pool[in], c->pool[in ^ 1], c->g, c->d_slots, c->d_order,
+                             c->num_active, elide ? c->d_lops[ord] : c->d_hops[ord],
+                             elide ? c->d_lbegin[ord] : c->d_hbegin[ord], recv, r.start, r.num,
+                             c->pc_start[r.start], c->p.stencil, elide, c->zf[in], c->zf[in ^ 1],
+                             c->d_zsrc[ord], c->stream);
+            else
+               launch_fused(c->pool[in], c->pool[in ^ 1], c->g, c->d_slots, c->d_order,
+                            c->num_active, c->d_hops[ord], c->d_hbegin[ord], recv, r.start, r.num,
+                            c->pc_start[r.start], c->p.stencil, c->stream);
          }
          if (c->num_active > 0) {
             c->cnt.kernel_launches++;
-            for (int v = r.start; v < r.start + r.num; v++) c->cur[v] ^= 1;
+            for (int v = r.start; v < r.start + r.num; v++) {
+               c->cur[v] ^= 1;
+               c->stale[v] = elide ? 1 : 0;
+               c->zf_ok[v] = elide ? 1 : 0;
+               c->stale_ord[v] = (signed char)ord;
+               c->stale_start[v] = c->pc_start[r.start];
+               if (elide) c->shell_synced[v] = 1;
+            }
          }
          for (int v = r.start; v < r.start + r.num; v++) c->pc_ord[v] = -1;
       } else {
+         CK(regen_ghosts(c, r.start, r.num));   // the in-place stencil reads the stored ghosts
+         for (int v = r.start; v < r.start + r.num; v++) c->zf_ok[v] = 0;
          KTimer t(c, KC_STENCIL);
          launch_stencil(c->pool[in], c->g, c->d_slots, c->num_active, r.start, r.num,
                         c->p.stencil, c->stream);
@@ -698,11 +848,19 @@ int flush_pending(mamr_ctx *c)
    return MAMR_OK;
 }
 
-// everything queued for [v0, v0+n) becomes visible in memory (ghost cells too)
-int settle(mamr_ctx *c, int v0, int n)
+// everything queued for [v0, v0+n) is applied to the interiors; a deferred comm()
+// becomes real.  Ghost cells an eliding launch skipped may still be stale.
+int settle_data(mamr_ctx *c, int v0, int n)
 {
    CK(flush_pending(c));
    return materialize_comm(c, v0, n);
+}
+
+// ... and every ghost cell in memory holds what the reference would hold
+int settle(mamr_ctx *c, int v0, int n)
+{
+   CK(settle_data(c, v0, n));
+   return regen_ghosts(c, v0, n);
 }
 
 int settle_all(mamr_ctx *c) { return settle(c, 0, c->p.num_vars); }
@@ -753,6 +911,8 @@ std::vector<int> processing_order(const mamr_ctx *c)
 void touch_all(mamr_ctx *c)
 {
    std::fill(c->cs_valid.begin(), c->cs_valid.end(), 0);
+   std::fill(c->shell_synced.begin(), c->shell_synced.end(), 0);
+   std::fill(c->zf_ok.begin(), c->zf_ok.end(), 0);
    c->modified_since_cs = true;
 }
 
@@ -801,14 +961,23 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
    c->cur.assign(p.num_vars, 0);
    c->pc_ord.assign(p.num_vars, -1);
    c->pc_start.assign(p.num_vars, 0);
+   c->stale.assign(p.num_vars, 0);
+   c->stale_ord.assign(p.num_vars, 0);
+   c->stale_start.assign(p.num_vars, 0);
+   c->shell_synced.assign(p.num_vars, 0);
+   c->zf_ok.assign(p.num_vars, 0);
    std::string err, why;
-   if (!stencil_configure(g, err) || !fused_configure(g, err)) {
+   if (!stencil_configure(g, err) || !fused_configure(g, err) || !fused2_configure(g, err)) {
       delete c;
       return fail(MAMR_EUNSUPPORTED, "%s", err.c_str());
    }
    c->fused_geom = fused_supported(g, why);
    const char *nf = getenv("MAMR_NO_FUSED");
    c->use_fused = !(nf && nf[0] == '1');
+   c->fused2_geom = c->fused_geom && fused2_supported(g);
+   const char *nf2 = getenv("MAMR_NO_FUSED2"), *ne = getenv("MAMR_NO_ELIDE");
+   c->use_fused2 = !(nf2 && nf2[0] == '1');
+   c->use_elide = !(ne && ne[0] == '1');
 #define CUC(call)                                                                         \
    do {                                                                                   \
       cudaError_t e_ = (call);                                                            \
@@ -824,6 +993,10 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
    for (int b = 0; b < 2; b++) {
       CUC(cudaMalloc(&c->pool[b], c->pool_bytes));
       CUC(cudaMemsetAsync(c->pool[b], 0, c->pool_bytes, c->stream));
+   }
+   if (c->fused2_geom && c->use_fused2 && c->use_elide) {
+      c->zf_bytes = (size_t)2*p.nx*p.ny*p.max_blocks*p.num_vars*sizeof(double);
+      for (int b = 0; b < 2; b++) CUC(cudaMalloc(&c->zf[b], c->zf_bytes));
    }
    CUC(cudaMalloc(&c->d_sums, p.num_vars*sizeof(double)));
    CUC(cudaMallocHost(&c->h_sums, p.num_vars*sizeof(double)));
@@ -847,9 +1020,14 @@ void mamr_destroy(mamr_ctx *c)
    if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
    cudaFree(c->pool[0]);
    cudaFree(c->pool[1]);
+   cudaFree(c->zf[0]);
+   cudaFree(c->zf[1]);
    for (int o = 0; o < 6; o++) {
       cudaFree(c->d_hops[o]);
       cudaFree(c->d_hbegin[o]);
+      cudaFree(c->d_lops[o]);
+      cudaFree(c->d_lbegin[o]);
+      cudaFree(c->d_zsrc[o]);
       for (int q = 0; q < 3; q++) cudaFree(c->d_pack[o][q]);
    }
    cudaFree(c->d_slots);
@@ -891,7 +1069,10 @@ int mamr_reset_counters(mamr_ctx *c)
 }
 
 long long mamr_tile_doubles(mamr_ctx *c) { return c ? c->g.tile : 0; }
-long long mamr_pool_bytes(mamr_ctx *c) { return c ? 2*(long long)c->pool_bytes : 0; }
+long long mamr_pool_bytes(mamr_ctx *c)
+{
+   return c ? 2*(long long)c->pool_bytes + (c->zf[0] ? 2*(long long)c->zf_bytes : 0) : 0;
+}
 
 // ---- block data in / out ---------------------------------------------------
 int mamr_upload_block(mamr_ctx *c, int slot, const double *tiles)
@@ -935,6 +1116,8 @@ int mamr_upload_tile(mamr_ctx *c, int slot, int var, const double *tile)
                       g.tile*sizeof(double), cudaMemcpyHostToDevice, c->stream));
    CU(cudaStreamSynchronize(c->stream));
    c->cs_valid[var] = 0;
+   c->shell_synced[var] = 0;
+   c->zf_ok[var] = 0;
    c->modified_since_cs = true;
    return MAMR_OK;
 }
@@ -1104,11 +1287,18 @@ int mamr_comm(mamr_ctx *c, int start, int num_comm, int stage)
    if (start < 0 || num_comm < 0 || start + num_comm > c->p.num_vars)
       return fail(MAMR_EINVAL, "comm: bad variable range [%d,%d)", start, start + num_comm);
    // a queued stencil or an earlier deferred comm() of these variables comes first
-   CK(settle(c, start, num_comm));
+   CK(settle_data(c, start, num_comm));
    if (c->ops_dirty) CK(build_ops(c));   // also validates the topology (comm.c:198-201)
    const int ord = order_index(c, stage);
    bool defer = false;
    CK(fused_ready(c, ord, &defer));
+   // Ghost cells an eliding launch left stale: this exchange overwrites every ghost
+   // cell it does not leave alone, and when its plan reads no stored ghost cell the
+   // old values are dead -- drop them.  Otherwise they become real first.
+   if (defer && c->plan[ord].elidable) {
+      for (int v = start; v < start + num_comm; v++) c->stale[v] = 0;
+   } else
+      CK(regen_ghosts(c, start, num_comm));
    if (defer) {
       // the fused kernel performs this exchange when the stencil of the variables
       // is launched; anything else that needs the ghost cells materialises it
@@ -1116,6 +1306,7 @@ int mamr_comm(mamr_ctx *c, int start, int num_comm, int stage)
          // the message buffers are about to be reused: an older deferred comm()
          // that still needs them becomes real first
          CK(materialize_comm(c, 0, c->p.num_vars));
+         CK(regen_ghosts(c, 0, c->p.num_vars));   // they may need the old messages
          // off-rank faces: per phase, fill the send buffers from resolved origins
          // (pack_face, comm.c:254-401) and exchange them (comm.c:71-84, 120-151)
          double *send[3] = { c->d_send[0], c->d_send[1], c->d_send[2] };

@@ -68,6 +68,13 @@ struct BoxOp {
    int first;            // index of the op's first cell in the block's flattened halo list
    short mode;           // FaceMode
    unsigned char dst_mem, src_mem;   // BoxMem
+   int flags;            // BoxFlag bits (halo plan only)
+};
+
+enum BoxFlag : int {
+   BF_IDENT = 1,       // ghost region no phase writes: the op copies the cell onto itself
+   BF_GHOST_SRC = 2,   // the source is a stored ghost cell (of this or another tile)
+   BF_FACE = 4         // destination is a pure face region (all the 7-point stencil reads)
 };
 
 // host copy of one direction of the reference's comm lists (comm.h:38-55)
@@ -91,6 +98,11 @@ struct HaloPlan {
    std::vector<BoxOp> ops;
    std::vector<int> begin;   // num_active + 1
    int max_ops = 0;          // largest op count of one block
+   // no op reads a stored ghost cell other than BF_IDENT ones: the stage result does
+   // not depend on the ghost cells in memory, so the fused kernel may leave the
+   // i-ghost planes and j-ghost rows of its output unwritten (api.cu regenerates
+   // them from the previous pool on demand)
+   bool elidable = false;
    bool ok = false;          // every ghost region resolved without an unsupported chain
    std::string why;          // reason when !ok
 };
@@ -133,6 +145,22 @@ void launch_fused(const double *pool_in, double *pool_out, const Geometry &g,
                   const int *d_begin,
                   const double *const recv[3], int var_start, int num_vars, int buf_var0,
                   int stencil, cudaStream_t s);
+// compile-time block size, trimmed tile traffic (fused2.cu)
+bool fused2_supported(const Geometry &g);
+bool fused2_configure(const Geometry &g, std::string &err);
+void launch_fused2(const double *pool_in, double *pool_out, const Geometry &g, const int *d_slots,
+                   const int *d_order, int num_active, const BoxOp *d_ops, const int *d_begin,
+                   const double *const recv[3], int var_start, int num_vars, int buf_var0,
+                   int stencil, bool elide, const double *zf_in, double *zf_out,
+                   const long long *d_zsrc, cudaStream_t s);
+// Z-face exports (the k=1 and k=nz interior planes of every tile, packed)
+void launch_zface_extract(const double *pool, double *zf, const Geometry &g, const int *d_slots,
+                          int num_active, int var_start, int num_vars, cudaStream_t s);
+// halo ops of every active block: pool_in (+ receive buffers) -> ghost cells of pool_out
+void launch_halo_fill(const BoxOp *d_ops, const int *d_begin, const int *d_slots, int num_active,
+                      const double *pool_in, double *pool_out, const Geometry &g,
+                      const double *const recv[3], int var_start, int num_vars, int buf_var0,
+                      bool only_ident, cudaStream_t s);
 // generic executor of BoxOps whose destination is a send buffer or the pool
 void launch_boxops(const BoxOp *d_ops, int n_ops, const double *pool_in, double *pool_out,
                    long long var_stride, double *const send[3], const double *const recv[3],

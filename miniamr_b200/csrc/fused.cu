@@ -27,27 +27,11 @@
 // separate ghost-exchange traffic 16 H/n^3 is fused away).
 #include "common.cuh"
 #include "ptx.cuh"
+#include "fused_common.cuh"
 
 namespace mamr {
 
 namespace {
-
-constexpr int FUSED_THREADS = 256;
-constexpr int MAX_OPS = 64;          // ops per block staged in shared memory
-
-struct FusedArgs {
-   const double *pool_in;
-   double *pool_out;
-   const int *slots;
-   const int *order;      // processing order: CTA -> active block index
-   const BoxOp *ops;
-   const int *begin;
-   const double *recv[3];
-   long long tile_stride, var_stride;
-   int num_active, var_start, var_end, vpc, buf_var0;
-   int nx, ny, nz;
-   int chunk;             // 27-point path: i-planes per thread
-};
 
 // 27-point path: a thread owns a 2x2 patch of (j,k) columns.  One i-plane of the
 // patch plus its ring is a 4x4 register tile (8 aligned 128-bit shared loads);
@@ -89,18 +73,6 @@ __device__ __forceinline__ void patch_sums(const double *__restrict__ p, int sj,
    out[2] = patch_sum9(P, 1, 0);
    out[3] = patch_sum9(P, 1, 1);
 }
-
-// compact copy of a BoxOp in shared memory
-struct SOp {
-   long long src_base, src_vs;
-   int first;                 // flattened index of its first element
-   int dst_base;
-   int e0, e1, e2;            // extents along i, j and k
-   int ds0, ds1, ds2;         // destination strides (tile strides)
-   int ss0, ss1, ss2;
-   int S, F;
-   int mode, src_mem;
-};
 
 // mbarrier wait with a C++-visible parity (phase) argument
 template <int STENCIL, int CPT, int Q>

@@ -182,6 +182,7 @@ void init_op(const Geometry &g, BoxOp &op)
    for (int ax = 0; ax < 3; ax++) op.dst_str[ax] = op.src_str[ax] = g.str[ax];
    op.S = op.F = 0;
    op.first = 0;
+   op.flags = 0;
    op.mode = FM_COPY;
    op.dst_mem = op.src_mem = BM_POOL;
 }
@@ -229,6 +230,7 @@ bool region_ops(Ctx &c, int a, const int r[3], std::vector<BoxOp> &ops)
       op.ext[ax] = r[ax] ? 1 : g.n[ax];
    }
    op.dst_base = cell_off(g, lo[0], lo[1], lo[2]);
+   if ((r[0] != 0) + (r[1] != 0) + (r[2] != 0) == 1) op.flags |= BF_FACE;
    // last phase that writes the region
    int o, d = -1;
    for (o = 2; o >= 0; o--) {
@@ -245,6 +247,10 @@ bool region_ops(Ctx &c, int a, const int r[3], std::vector<BoxOp> &ops)
       Origin og;
       if (!resolve(c, a, cc, 3, og)) return false;
       origin_op(c, og, op.ext, op);
+      if (o < 0) op.flags |= BF_IDENT | BF_GHOST_SRC;
+      else if (og.kind == 0)
+         for (int ax = 0; ax < 3; ax++)
+            if (og.cc[ax] >= 0 && is_ghost(g, ax, og.cc[ax])) op.flags |= BF_GHOST_SRC;
       ops.push_back(op);
       return true;
    }
@@ -383,6 +389,9 @@ void build_halo_plan(const PlanInput &in, HaloPlan &out)
       }
       out.max_ops = std::max(out.max_ops, out.begin[a + 1] - out.begin[a]);
    }
+   out.elidable = true;
+   for (const BoxOp &op : out.ops)
+      if ((op.flags & BF_GHOST_SRC) && !(op.flags & BF_IDENT)) out.elidable = false;
    out.ok = true;
 }
 

@@ -45,7 +45,8 @@ def test_stage_loop_matches_golden_bit_exact(name):
     d.close()
 
 
-@pytest.mark.parametrize("name", ["amr7_moved_permute", "uni27_permute", "cfg3_like_ring"])
+@pytest.mark.parametrize("name", ["amr7_moved_permute", "uni27_permute", "cfg3_like_ring",
+                                  "cfg2_like"])
 def test_each_call_matches_oracle(name):
     """Finer-grained than the golden digest: compare after every comm() and every
     stencil_driver() against the oracle, so a failure names the routine."""
@@ -189,4 +190,90 @@ def test_conservation_at_full_size_cfg2():
         d.stage(st)
     s1 = d.check_sum_vars(0, V)
     assert np.all(np.abs(s1 - s0)/s0 < 1e-12)
+    d.close()
+
+
+@pytest.mark.parametrize("topo,n,stencil,check_every", [
+    ("amr7_aniso", 16, 7, 1), ("amr7_aniso", 16, 7, 3), ("cfg1_like", 16, 7, 2),
+    ("uni27_aniso", 16, 27, 1), ("uni27_aniso", 16, 27, 3), ("amr7_moved_permute", 16, 7, 2)])
+def test_fixed_size_kernel_and_ghost_elision_vs_oracle(topo, n, stencil, check_every):
+    """The compile-time-size fused kernel (fused2.cu) on the topologies of the golden
+    meshes (a topology does not depend on the block size): level boundaries, domain
+    boundaries, never-written edge regions.  Tiles are seeded with random GHOST cells
+    too, and downloaded only every `check_every` stages, so that the ghost layers an
+    eliding launch leaves stale (api.cu: regen_ghosts) are compared bit for bit with
+    what the reference holds."""
+    from miniamr_b200.capi import DeviceMesh
+    g = Golden(topo)
+    V = 3
+    slots = g.slots if topo != "cfg1_like" else g.slots[:]
+    d = DeviceMesh(n, n, n, V, g.max_blocks, stencil=stencil, comm_vars=2, permute=g.permute)
+    m = OracleMesh(n, n, n, V, g.max_blocks, stencil=stencil, comm_vars=2, permute=g.permute)
+    d.set_topology(g.slots, g.level, g.nei_level, g.nei)
+    m.set_topology(g.slots, g.level, g.nei_level, g.nei)
+    rs = np.random.RandomState(11)
+    for s in slots:
+        t = rs.random_sample((V, n + 2, n + 2, n + 2))
+        d.upload_block(int(s), t)
+        m.data[int(s)] = t
+    stages = 4 if topo != "cfg1_like" else 2
+    for st in range(stages):
+        for start in range(0, V, 2):
+            num = min(2, V - start)
+            d.comm(start, num, st)
+            for v in range(start, start + num):
+                d.stencil_driver(v, st)
+        m.stage(st)
+        if (st + 1) % check_every == 0 or st == stages - 1:
+            for s in slots:
+                got = d.download_block(int(s))
+                bad = bits(got) != bits(m.data[int(s)])
+                assert not bad.any(), (f"stage {st} slot {s}: {int(bad.sum())} cells differ, "
+                                       f"first {np.argwhere(bad)[0]}")
+        for v in range(V):
+            want = m.check_sum(v)
+            assert abs(d.check_sum(v) - want) <= CS_RTOL*abs(want)
+    c = d.counters()
+    assert c["kernel_launches"] > 0
+    d.close()
+
+
+def test_elision_state_machine_edge_cases():
+    """Calls that do not follow the driver's comm -> stencil pattern while ghost
+    layers are stale: a second stencil without a comm, comm on a sub-range, a
+    download between comm and stencil, upload of one tile."""
+    from miniamr_b200.capi import DeviceMesh
+    from miniamr_b200.mesh import uniform_mesh
+    n, V, B = 16, 4, 2
+    top = uniform_mesh(B, B, B)
+    d = DeviceMesh(n, n, n, V, B**3 + 2, stencil=27)
+    m = OracleMesh(n, n, n, V, B**3 + 2, stencil=27)
+    d.set_topology(top["slots"], top["level"], top["nei_level"], top["nei"])
+    m.set_topology(top["slots"], top["level"], top["nei_level"], top["nei"])
+    rs = np.random.RandomState(5)
+    for s in top["slots"]:
+        t = rs.random_sample((V, n + 2, n + 2, n + 2))
+        d.upload_block(int(s), t)
+        m.data[int(s)] = t
+
+    def same(what):
+        for s in top["slots"]:
+            bad = bits(d.download_block(int(s))) != bits(m.data[int(s)])
+            assert not bad.any(), f"{what}: slot {s}: {int(bad.sum())} cells differ, first {np.argwhere(bad)[0]}"
+
+    d.stage(0); m.stage(0)
+    d.stage(1); m.stage(1)                        # ghosts stale for two stages
+    d.stencil_driver(1, 2); m.stencil_driver(1, 2)    # stencil without a comm
+    same("stencil without comm")
+    d.stage(2); m.stage(2)
+    d.comm(1, 2, 3); m.comm(1, 2, 3)              # sub-range comm, then look
+    same("sub-range comm")
+    for v in (1, 2):
+        d.stencil_driver(v, 3); m.stencil_driver(v, 3)
+    d.stage(4); m.stage(4)
+    t = rs.random_sample((n + 2, n + 2, n + 2))
+    d.upload_tile(3, 2, t); m.data[3][2] = t      # one tile replaced while ghosts are stale
+    d.stage(5); m.stage(5)
+    same("after upload_tile")
+    assert d.counters()["ghost_regens"] > 0
     d.close()

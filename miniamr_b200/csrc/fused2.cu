@@ -219,6 +219,11 @@ fused2_kernel(const FusedArgs A)
          if (mode != FM_COPY || s.src_mem != BM_POOL) plain = false;
          // perf experiments only (MAMR_DEBUG_SKIP): drop the Z-face cells / every cell
          if (((A.chunk & 1) && dsto >= TILE) || (A.chunk & 2)) dinfo[q] = -1;
+         if (dsto < TILE) {
+            const int dk = dsto%SJ;
+            const bool kg = dk == 0 || dk == N + 1;
+            if (((A.chunk & 4) && kg) || ((A.chunk & 8) && !kg)) dinfo[q] = -1;
+         }
       }
    }
    const int nplain = __popc(__ballot_sync(0xffffffffu, plain));

@@ -26,6 +26,10 @@ CASES = [
     dict(np=[1, 1, 2], n=[4, 4, 6], b=[3, 2, 2], vars=2, stencil=27, stages=7, seed=4, permute=1),
     dict(np=[1, 1, 2], n=[16, 16, 16], b=[2, 2, 2], vars=2, stencil=27, stages=2, seed=5),
     dict(np=[2, 1, 1], n=[10, 10, 10], b=[2, 2, 2], vars=5, stencil=7, stages=3, seed=6, comm_vars=2),
+    # the fixed-size kernel with ghost elision: several comm() groups per stage (stale ghost
+    # layers of the other groups must survive the reuse of the receive buffers), 7-point
+    dict(np=[2, 1, 1], n=[16, 16, 16], b=[2, 2, 3], vars=5, stencil=27, stages=3, seed=7, comm_vars=2),
+    dict(np=[1, 2, 1], n=[16, 16, 16], b=[2, 2, 2], vars=3, stencil=7, stages=3, seed=8),
 ]
 
 

@@ -76,25 +76,31 @@ template <int N>
 struct Shape {
    static constexpr int SJ = N + 2, PL = SJ*SJ, TILE = (N + 2)*PL;
    static constexpr int HALO = TILE - N*N*N;
-   static constexpr int Q = (HALO + FUSED_THREADS - 1)/FUSED_THREADS;
+   // compute threads per CTA: small tiles take fewer threads and more CTAs per SM
+   static constexpr int CT = N >= 14 ? 256 : (N >= 10 ? 128 : 64);
+   static constexpr int THREADS = CT + 32;        // + the copy warp
+   static constexpr int Q = (HALO + CT - 1)/CT;
    // Z-face cells (k = 0 and N+1 of rows 1..N, planes 1..N) lie inside the rows the
    // bulk copy writes: they are gathered into a staging area behind the tile and
    // patched in once the tile has landed
    static constexpr int ZST = 2*N*N;
-   static constexpr int ZPT = (ZST + FUSED_THREADS - 1)/FUSED_THREADS;
+   static constexpr int ZPT = (ZST + CT - 1)/CT;
    // ... and the k=1 / k=N planes of the updated tile are packed into a second area
    // of the same size, from where they are exported (Z-face pool)
    static constexpr int TB = TILE + 2*ZST;        // doubles per buffer
    // 27-point: 2x2 patches x chunks of CH planes
    static constexpr int GROUPS = (N/2)*(N/2);
-   static constexpr int NCH = FUSED_THREADS/GROUPS > N ? N : FUSED_THREADS/GROUPS;
+   static constexpr int NCH = CT/GROUPS > N ? N : CT/GROUPS;
    static constexpr int CH = (N + NCH - 1)/NCH;
    // 7-point: (j,k) columns
-   static constexpr int CPT = (N*N + FUSED_THREADS - 1)/FUSED_THREADS;
+   static constexpr int CPT = (N*N + CT - 1)/CT;
    static constexpr int SMEM = 2*TB*8 + MAX_OPS*(int)sizeof(SOp) + 64;
+   // CTAs per SM: shared memory (1 KB reserved per CTA), 96 registers per thread
+   static constexpr int BY_SMEM = (228*1024)/(SMEM + 128 + 1024);
+   static constexpr int BY_REGS = 65536/(96*THREADS);
+   static constexpr int CTAS = BY_SMEM < BY_REGS ? (BY_SMEM < 8 ? BY_SMEM : 8) : (BY_REGS < 8 ? BY_REGS : 8);
 };
 
-constexpr int F2_THREADS = FUSED_THREADS + 32;   // 8 compute warps + 1 copy warp
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
@@ -102,11 +108,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 }
 
 template <int ST, int N, bool ELIDE>
-__global__ void __launch_bounds__(F2_THREADS, 2)
+__global__ void __launch_bounds__(Shape<N>::THREADS, Shape<N>::CTAS)
 fused2_kernel(const FusedArgs A)
 {
    using S = Shape<N>;
-   constexpr int SJ = S::SJ, PL = S::PL, TILE = S::TILE, Q = S::Q, TB = S::TB;
+   constexpr int SJ = S::SJ, PL = S::PL, TILE = S::TILE, Q = S::Q, TB = S::TB, CT = S::CT;
    extern __shared__ __align__(128) unsigned char smem_raw[];
    double *buf0 = reinterpret_cast<double *>(smem_raw);
    SOp *sops = reinterpret_cast<SOp *>(smem_raw + (size_t)2*TB*8);
@@ -126,18 +132,18 @@ fused2_kernel(const FusedArgs A)
    if (tid == 0) {
       mbar_init(&full[0], 1);
       mbar_init(&full[1], 1);
-      mbar_init(&done[0], FUSED_THREADS/32);
-      mbar_init(&done[1], FUSED_THREADS/32);
+      mbar_init(&done[0], CT/32);
+      mbar_init(&done[1], CT/32);
       fence_barrier_init();
    }
    stage_ops(A.ops + ob, nops, sops, tid);
    __syncthreads();
 
    constexpr uint32_t ROWS_BYTES = (uint32_t)N*SJ*8u;
-   if (tid >= FUSED_THREADS) {
+   if (tid >= CT) {
       // ---- copy warp: every bulk copy of the CTA is issued here, so no compute
       // warp ever waits for a store to drain or spends issue slots on UBLKCP ----
-      if (tid != FUSED_THREADS) return;
+      if (tid != CT) return;
       // rows 1..N of planes 1..N: one bulk copy per plane
       constexpr uint32_t ZF_BYTES = (uint32_t)N*N*8u;
       long long zs[2] = { -1, -1 };
@@ -188,7 +194,7 @@ fused2_kernel(const FusedArgs A)
    bool plain = true;     // every cell of this thread: 8-byte copy out of the pool
 #pragma unroll
    for (int q = 0; q < Q; q++) {
-      const int e = tid + q*FUSED_THREADS;
+      const int e = tid + q*CT;
       soff[q] = 0;
       dinfo[q] = -1;
       if (e < E) {
@@ -229,9 +235,9 @@ fused2_kernel(const FusedArgs A)
    const int nplain = __popc(__ballot_sync(0xffffffffu, plain));
    __shared__ int s_notplain;
    if (tid == 0) s_notplain = 0;
-   named_bar_sync(1, FUSED_THREADS);
+   named_bar_sync(1, CT);
    if (nplain != 32 && (tid & 31) == 0) atomicAdd(&s_notplain, 1);
-   named_bar_sync(1, FUSED_THREADS);
+   named_bar_sync(1, CT);
    const bool simple = s_notplain == 0;
 
    // halo cell q of this thread for variable v -> buffer dst
@@ -299,7 +305,7 @@ fused2_kernel(const FusedArgs A)
    bool live[S::CPT];
 #pragma unroll
    for (int q = 0; q < S::CPT; q++) {
-      const int c = tid + q*FUSED_THREADS;
+      const int c = tid + q*CT;
       live[q] = c < N*N;
       const int cc = live[q] ? c : 0;
       coff[q] = (cc/N + 1)*SJ + cc%N + 1;
@@ -311,10 +317,10 @@ fused2_kernel(const FusedArgs A)
       if (ELIDE) {
          mbar_wait(&full[t & 1], (uint32_t)((t >> 1) & 1));
          cp_async_wait_all();
-         named_bar_sync(1, FUSED_THREADS);       // every thread's staged Z cells are visible
+         named_bar_sync(1, CT);       // every thread's staged Z cells are visible
 #pragma unroll
          for (int z = 0; z < S::ZPT; z++) {
-            const int sl = tid + z*FUSED_THREADS;
+            const int sl = tid + z*CT;
             if (sl < S::ZST) {
                const int side = sl/(N*N), rem = sl - side*(N*N);
                sm[(rem/N + 1)*PL + (rem%N + 1)*SJ + side*(N + 1)] = sm[TILE + sl];
@@ -328,7 +334,7 @@ fused2_kernel(const FusedArgs A)
          pre = false;
          cp_async_wait_all();
       }
-      named_bar_sync(1, FUSED_THREADS);
+      named_bar_sync(1, CT);
 
       if (ST == 7) {
          double r[S::CPT][N];
@@ -353,7 +359,7 @@ fused2_kernel(const FusedArgs A)
             }
             if (q == S::CPT/2) prefetch_halo(t);
          }
-         named_bar_sync(1, FUSED_THREADS);       // the old tile has been read by everyone
+         named_bar_sync(1, CT);       // the old tile has been read by everyone
 #pragma unroll
          for (int q = 0; q < S::CPT; q++) {
             if (!live[q]) continue;
@@ -372,7 +378,7 @@ fused2_kernel(const FusedArgs A)
             for (int i = 0; i < N; i++) c[(i + 1)*PL] = r[q][i];
             if (ELIDE) {
                // columns k=1 and k=N are the Z-face exports of this tile
-               const int cc = tid + q*FUSED_THREADS, cj = cc/N, ck = cc%N;
+               const int cc = tid + q*CT, cj = cc/N, ck = cc%N;
                if (ck == 0 || ck == N - 1) {
                   double *z = sm + TILE + S::ZST + (ck ? N*N : 0) + cj;
 #pragma unroll
@@ -407,7 +413,7 @@ fused2_kernel(const FusedArgs A)
             if (ELIDE && t + 1 < nv) gather(v + 1, buf0 + (size_t)((t + 1) & 1)*TB);
             prefetch_halo(t);
          }
-         named_bar_sync(1, FUSED_THREADS);       // the old tile has been read by everyone
+         named_bar_sync(1, CT);       // the old tile has been read by everyone
          if (pact) {
             // the two cells of a row pair are stored in an order that alternates with
             // the patch row: a half-warp then covers all 16 8-byte banks
@@ -453,11 +459,11 @@ template <int N>
 constexpr bool shape_ok()
 {
    using S = Shape<N>;
-   return (N%2) == 0 && S::SMEM <= 113*1024 && S::TILE < (1 << 20) && S::NCH >= 1 &&
-          S::GROUPS*S::NCH <= FUSED_THREADS;
+   return (N%2) == 0 && S::CTAS >= 2 && S::TILE < (1 << 20) && S::NCH >= 1 &&
+          S::GROUPS*S::NCH <= S::CT;
 }
 
-#define MAMR_FUSED2_SIZES(X) X(16)
+#define MAMR_FUSED2_SIZES(X) X(8) X(10) X(12) X(16)
 
 template <int ST, int N, bool EL>
 cudaError_t set_attr2()
@@ -534,11 +540,11 @@ void launch_fused2(const double *pool_in, double *pool_out, const Geometry &g, c
    if (g.n[0] == NN) {                                                                        \
       const int sm = Shape<NN>::SMEM;                                                         \
       if (stencil == 7) {                                                                     \
-         if (elide) fused2_kernel<7, NN, true><<<grid, F2_THREADS, sm, s>>>(A);            \
-         else fused2_kernel<7, NN, false><<<grid, F2_THREADS, sm, s>>>(A);                 \
+         if (elide) fused2_kernel<7, NN, true><<<grid, Shape<NN>::THREADS, sm, s>>>(A);            \
+         else fused2_kernel<7, NN, false><<<grid, Shape<NN>::THREADS, sm, s>>>(A);                 \
       } else {                                                                                \
-         if (elide) fused2_kernel<27, NN, true><<<grid, F2_THREADS, sm, s>>>(A);           \
-         else fused2_kernel<27, NN, false><<<grid, F2_THREADS, sm, s>>>(A);                \
+         if (elide) fused2_kernel<27, NN, true><<<grid, Shape<NN>::THREADS, sm, s>>>(A);           \
+         else fused2_kernel<27, NN, false><<<grid, Shape<NN>::THREADS, sm, s>>>(A);                \
       }                                                                                       \
    }
    MAMR_FUSED2_SIZES(X)

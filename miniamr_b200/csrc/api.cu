@@ -130,6 +130,14 @@ struct mamr_ctx {
    size_t zf_bytes = 0;
    std::vector<char> zf_ok;
    long long *d_zsrc[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+   // streamed 7-point kernel (slab7.cu): per phase order, the plain faces of every
+   // block and the cell ops of the others
+   bool slab_geom = false;
+   bool use_slab = true;        // MAMR_NO_SLAB=1
+   bool slab_ok[6] = {false, false, false, false, false, false};
+   long long *d_fsrc[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+   BoxOp *d_cops[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+   int *d_cbegin[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
    BoxOp *d_lops[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // lean op lists
    int *d_lbegin[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
    bool plan_has_ident[6] = {false, false, false, false, false, false};
@@ -629,6 +637,71 @@ int materialize_comm(mamr_ctx *c, int v0, int n)
    return MAMR_OK;
 }
 
+// Streamed 7-point kernel: classify the six faces of every block.  A face that is
+// a plain copy of a same-level neighbour's (or, at a reflective boundary, the
+// block's own) interior plane is described by ONE source offset and fetched by bulk
+// copies; any other face must consist of FM_COPY ops, executed cell by cell.
+int build_slab_plan(mamr_ctx *c, int ord)
+{
+   const HaloPlan &P = c->plan[ord];
+   for (void *p : { (void *)c->d_fsrc[ord], (void *)c->d_cops[ord], (void *)c->d_cbegin[ord] })
+      if (p) CU(cudaFree(p));
+   c->d_fsrc[ord] = nullptr; c->d_cops[ord] = nullptr; c->d_cbegin[ord] = nullptr;
+   c->slab_ok[ord] = false;
+   if (!c->slab_geom || !c->use_slab || !c->use_elide || c->p.stencil != 7 || !P.ok || !P.elidable)
+      return MAMR_OK;
+   const Geometry &g = c->g;
+   const int N = g.n[0];
+   const long long PL = g.str[0], SJ = g.str[1];
+   const size_t nb = P.begin.size() - 1;
+   std::vector<long long> fsrc(6*std::max<size_t>(1, nb), -1);
+   std::vector<BoxOp> cops;
+   std::vector<int> cbegin(nb + 1, 0);
+   auto cell = [&](int i, int j, int k) { return (long long)i*PL + j*SJ + k; };
+   for (size_t a = 0; a < nb; a++) {
+      cbegin[a] = (int)cops.size();
+      for (int o = P.begin[a]; o < P.begin[a + 1]; o++) {
+         const BoxOp &op = P.ops[o];
+         if (!(op.flags & BF_FACE)) continue;          // the 7-point stencil reads faces only
+         if (op.mode != FM_COPY) return MAMR_OK;       // level boundary: not streamed
+         int f = -1;
+         if (op.ext[0] == 1 && op.ext[1] == N && op.ext[2] == N)
+            f = op.dst_base == cell(0, 1, 1) ? 0 : (op.dst_base == cell(N + 1, 1, 1) ? 1 : -1);
+         else if (op.ext[0] == N && op.ext[1] == 1 && op.ext[2] == N)
+            f = op.dst_base == cell(1, 0, 1) ? 2 : (op.dst_base == cell(1, N + 1, 1) ? 3 : -1);
+         else if (op.ext[0] == N && op.ext[1] == N && op.ext[2] == 1)
+            f = op.dst_base == cell(1, 1, 0) ? 4 : (op.dst_base == cell(1, 1, N + 1) ? 5 : -1);
+         const bool plain = f >= 0 && op.src_mem == BM_POOL && !(op.flags & BF_GHOST_SRC) &&
+                            op.src_str[0] == PL && op.src_str[1] == SJ && op.src_str[2] == 1;
+         if (plain) {
+            const long long m = op.src_base/g.tile_stride, sc = op.src_base%g.tile_stride;
+            if (f < 2) { fsrc[6*a + f] = op.src_base - 1; continue; }
+            if (f < 4) { fsrc[6*a + f] = op.src_base - 1 - PL; continue; }
+            if (sc == cell(1, 1, 1) || sc == cell(1, 1, N)) {
+               fsrc[6*a + f] = m*2LL*N*N + (sc == cell(1, 1, 1) ? 0 : (long long)N*N);
+               continue;
+            }
+         }
+         cops.push_back(op);
+      }
+      if ((int)cops.size() - cbegin[a] > slab7_max_cell_ops()) return MAMR_OK;
+   }
+   cbegin[nb] = (int)cops.size();
+   CU(cudaMalloc(&c->d_fsrc[ord], fsrc.size()*sizeof(long long)));
+   CU(cudaMalloc(&c->d_cops[ord], std::max<size_t>(1, cops.size())*sizeof(BoxOp)));
+   CU(cudaMalloc(&c->d_cbegin[ord], cbegin.size()*sizeof(int)));
+   CU(cudaMemcpyAsync(c->d_fsrc[ord], fsrc.data(), fsrc.size()*sizeof(long long),
+                      cudaMemcpyHostToDevice, c->stream));
+   if (!cops.empty())
+      CU(cudaMemcpyAsync(c->d_cops[ord], cops.data(), cops.size()*sizeof(BoxOp),
+                         cudaMemcpyHostToDevice, c->stream));
+   CU(cudaMemcpyAsync(c->d_cbegin[ord], cbegin.data(), cbegin.size()*sizeof(int),
+                      cudaMemcpyHostToDevice, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   c->slab_ok[ord] = true;
+   return MAMR_OK;
+}
+
 // build (once per topology and phase order) the halo plan of the fused kernel
 int ensure_plan(mamr_ctx *c, int ord)
 {
@@ -718,6 +791,7 @@ int ensure_plan(mamr_ctx *c, int ord)
                          cudaMemcpyHostToDevice, c->stream));
       CU(cudaStreamSynchronize(c->stream));   // the host vectors go out of scope
    }
+   CK(build_slab_plan(c, ord));
    for (int o = 0; o < 3; o++) {
       if (c->d_pack[ord][o]) CU(cudaFree(c->d_pack[ord][o]));
       c->d_pack[ord][o] = nullptr;
@@ -735,10 +809,10 @@ int ensure_plan(mamr_ctx *c, int ord)
 int fused_ready(mamr_ctx *c, int ord, bool *yes)
 {
    *yes = false;
-   if (!c->use_fused || !c->fused_geom || c->num_active == 0) return MAMR_OK;
+   if (!c->use_fused || !(c->fused_geom || c->slab_geom) || c->num_active == 0) return MAMR_OK;
    if (c->have_partners && !c->nccl) return MAMR_OK;   // comm_split reports the error
    CK(ensure_plan(c, ord));
-   *yes = c->plan[ord].ok;
+   *yes = c->plan[ord].ok && (c->fused_geom || c->slab_ok[ord]);
    return MAMR_OK;
 }
 
@@ -782,8 +856,9 @@ int flush_pending(mamr_ctx *c)
       if (ord >= 0) {
          // comm() + stencil in one pass: current pool -> other pool
          const double *recv[3] = { c->d_recv[0], c->d_recv[1], c->d_recv[2] };
+         const bool slab = c->slab_ok[ord];
          const bool f2 = c->fused2_geom && c->use_fused2;
-         const bool elide = f2 && c->use_elide && c->plan[ord].elidable && c->d_lops[ord];
+         const bool elide = slab || (f2 && c->use_elide && c->plan[ord].elidable && c->d_lops[ord]);
          if (elide && c->plan_has_ident[ord] && c->num_active > 0) {
             // never-written ghost regions: the output pool must already hold them
             bool synced = true;
@@ -812,7 +887,12 @@ int flush_pending(mamr_ctx *c)
          }
          {
             KTimer t(c, KC_STENCIL);
-            if (f2)
+            if (slab)
+               launch_slab7(c->pool[in], c->pool[in ^ 1], c->g, c->d_slots, c->d_order,
+                            c->num_active, c->d_fsrc[ord], c->d_cops[ord], c->d_cbegin[ord], recv,
+                            r.start, r.num, c->pc_start[r.start], c->zf[in], c->zf[in ^ 1],
+                            c->stream);
+            else if (f2)
                launch_fused2(c->pool[in], c->pool[in ^ 1], c->g, c->d_slots, c->d_order,
                              c->num_active, elide ? c->d_lops[ord] : c->d_hops[ord],
                              elide ? c->d_lbegin[ord] : c->d_hbegin[ord], recv, r.start, r.num,
@@ -967,7 +1047,8 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
    c->shell_synced.assign(p.num_vars, 0);
    c->zf_ok.assign(p.num_vars, 0);
    std::string err, why;
-   if (!stencil_configure(g, err) || !fused_configure(g, err) || !fused2_configure(g, err)) {
+   if (!stencil_configure(g, err) || !fused_configure(g, err) || !fused2_configure(g, err) ||
+       !slab7_configure(g, err)) {
       delete c;
       return fail(MAMR_EUNSUPPORTED, "%s", err.c_str());
    }
@@ -994,7 +1075,10 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
       CUC(cudaMalloc(&c->pool[b], c->pool_bytes));
       CUC(cudaMemsetAsync(c->pool[b], 0, c->pool_bytes, c->stream));
    }
-   if (c->fused2_geom && c->use_fused2 && c->use_elide) {
+   const char *nsl = getenv("MAMR_NO_SLAB");
+   c->use_slab = !(nsl && nsl[0] == '1');
+   c->slab_geom = p.stencil == 7 && slab7_supported(g) && c->use_fused && c->use_slab && c->use_elide;
+   if ((c->fused2_geom && c->use_fused2 && c->use_elide) || c->slab_geom) {
       c->zf_bytes = (size_t)2*p.nx*p.ny*p.max_blocks*p.num_vars*sizeof(double);
       for (int b = 0; b < 2; b++) CUC(cudaMalloc(&c->zf[b], c->zf_bytes));
    }
@@ -1028,6 +1112,9 @@ void mamr_destroy(mamr_ctx *c)
       cudaFree(c->d_lops[o]);
       cudaFree(c->d_lbegin[o]);
       cudaFree(c->d_zsrc[o]);
+      cudaFree(c->d_fsrc[o]);
+      cudaFree(c->d_cops[o]);
+      cudaFree(c->d_cbegin[o]);
       for (int q = 0; q < 3; q++) cudaFree(c->d_pack[o][q]);
    }
    cudaFree(c->d_slots);

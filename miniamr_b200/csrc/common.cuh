@@ -156,6 +156,14 @@ void launch_fused2(const double *pool_in, double *pool_out, const Geometry &g, c
 // Z-face exports (the k=1 and k=nz interior planes of every tile, packed)
 void launch_zface_extract(const double *pool, double *zf, const Geometry &g, const int *d_slots,
                           int num_active, int var_start, int num_vars, cudaStream_t s);
+// 7-point stencil on tiles too big for shared memory: planes streamed (slab7.cu)
+bool slab7_supported(const Geometry &g);
+bool slab7_configure(const Geometry &g, std::string &err);
+int slab7_max_cell_ops();
+void launch_slab7(const double *pool_in, double *pool_out, const Geometry &g, const int *d_slots,
+                  const int *d_order, int num_active, const long long *d_fsrc, const BoxOp *d_cops,
+                  const int *d_cbegin, const double *const recv[3], int var_start, int num_vars,
+                  int buf_var0, const double *zf_in, double *zf_out, cudaStream_t s);
 // halo ops of every active block: pool_in (+ receive buffers) -> ghost cells of pool_out
 void launch_halo_fill(const BoxOp *d_ops, const int *d_begin, const int *d_slots, int num_active,
                       const double *pool_in, double *pool_out, const Geometry &g,

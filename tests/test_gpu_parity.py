@@ -197,7 +197,10 @@ def test_conservation_at_full_size_cfg2():
     ("amr7_aniso", 16, 7, 1), ("amr7_aniso", 16, 7, 3), ("cfg1_like", 16, 7, 2),
     ("uni27_aniso", 16, 27, 1), ("uni27_aniso", 16, 27, 3), ("amr7_moved_permute", 16, 7, 2),
     ("amr7_aniso", 10, 7, 2), ("uni27_aniso", 10, 27, 2), ("amr7_aniso", 8, 7, 1),
-    ("uni27_aniso", 8, 27, 3), ("uni27_aniso", 12, 27, 3), ("amr7_moved_permute", 12, 7, 1)])
+    ("uni27_aniso", 8, 27, 3), ("uni27_aniso", 12, 27, 3), ("amr7_moved_permute", 12, 7, 1),
+    # 32^3 tiles: the streamed 7-point kernel (slab7.cu) on a uniform mesh, the split path
+    # on a refined one
+    ("uni27_aniso", 32, 7, 1), ("uni27_aniso", 32, 7, 4), ("amr7_aniso", 32, 7, 2)])
 def test_fixed_size_kernel_and_ghost_elision_vs_oracle(topo, n, stencil, check_every):
     """The compile-time-size fused kernel (fused2.cu) on the topologies of the golden
     meshes (a topology does not depend on the block size): level boundaries, domain

@@ -30,6 +30,10 @@ CASES = [
     # layers of the other groups must survive the reuse of the receive buffers), 7-point
     dict(np=[2, 1, 1], n=[16, 16, 16], b=[2, 2, 3], vars=5, stencil=27, stages=3, seed=7, comm_vars=2),
     dict(np=[1, 2, 1], n=[16, 16, 16], b=[2, 2, 2], vars=3, stencil=7, stages=3, seed=8),
+    # streamed 7-point kernel: off-rank faces in X, Y and Z (cells out of the receive buffers)
+    dict(np=[2, 1, 1], n=[32, 32, 32], b=[1, 2, 2], vars=3, stencil=7, stages=3, seed=9, comm_vars=2),
+    dict(np=[1, 2, 1], n=[32, 32, 32], b=[2, 1, 2], vars=2, stencil=7, stages=3, seed=10),
+    dict(np=[1, 1, 2], n=[32, 32, 32], b=[2, 2, 1], vars=2, stencil=7, stages=3, seed=11),
 ]
 
 

@@ -159,12 +159,26 @@ int mamr_unpack_block(mamr_ctx *ctx, int slot, const double *payload);
  * rcb.c:237,261): both ranks call, one as sender one as receiver */
 int mamr_send_block(mamr_ctx *ctx, int slot, int dest_rank);
 int mamr_recv_block(mamr_ctx *ctx, int slot, int src_rank);
+/* The form the drop-in uses under the reference's blocking pairwise handshake
+ * (exchange(), rcb.c:207-337): the sender packs the payload into a device
+ * staging area at pack_block() time (its slot is reused right away,
+ * rcb.c:259-266), the receiver records (slot, source) at unpack_block() time,
+ * and every rank calls mamr_flush_block_moves() at the same point of the
+ * program afterwards (end of move_blocks(), rcb.c:734-): ONE NCCL group with
+ * all sends and receives, then the unpack kernels.  Between one pair of ranks
+ * the k-th staged send matches the k-th staged receive. */
+int mamr_stage_send_block(mamr_ctx *ctx, int slot, int dest_rank);
+int mamr_stage_recv_block(mamr_ctx *ctx, int slot, int src_rank);
+int mamr_flush_block_moves(mamr_ctx *ctx);
+int mamr_pending_block_moves(mamr_ctx *ctx);      /* staged and not yet flushed */
 
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink ------------------- */
 #define MAMR_NCCL_ID_BYTES 128
 int mamr_nccl_get_unique_id(char id[MAMR_NCCL_ID_BYTES]);   /* rank 0, then broadcast
                                                                over the host channel */
 int mamr_nccl_init(mamr_ctx *ctx, const char id[MAMR_NCCL_ID_BYTES]);
+int mamr_device_count(void);        /* visible CUDA devices (0 without a driver): lets a
+                                       host without CUDA headers map rank -> device */
 
 /* ---- host-only view of the halo plan (no device needed; tests and tools) --
  * The plan is what the fused stage kernel executes for one comm() call: for

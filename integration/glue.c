@@ -43,6 +43,7 @@ static int topo_dirty = 1;      /* device descriptors older than blocks[]/comm l
 static int host_fresh = 1;      /* blocks[].array holds data the device has not seen */
 static mamr_counters seen;      /* counters already added to the reference's globals */
 static double *stage_tile;      /* one block, [var][i][j][k] contiguous            */
+static int nccl_moves;          /* migrated block payloads travel GPU to GPU (NCCL)   */
 
 static void die(const char *where)
 {
@@ -68,7 +69,21 @@ static void ensure_ctx(void)
    p.stencil = stencil; p.code = code; p.permute = permute;
    p.device = -1; p.rank = my_pe; p.num_ranks = num_pes;
    if (getenv("MAMR_DEVICE")) p.device = atoi(getenv("MAMR_DEVICE"));
+   else if (num_pes > 1) {
+      /* one rank per GPU of the node, rank r <-> GPU r */
+      int ndev = mamr_device_count();
+      if (ndev > 0) p.device = my_pe%ndev;
+   }
    OK(mamr_create(&p, &G), "create");
+   if (num_pes > 1) {
+      /* the NCCL id travels over the host channel, like every other piece of metadata */
+      char id[MAMR_NCCL_ID_BYTES];
+      memset(id, 0, sizeof id);
+      if (!my_pe) OK(mamr_nccl_get_unique_id(id), "nccl_get_unique_id");
+      MPI_Bcast(id, MAMR_NCCL_ID_BYTES, MPI_CHAR, 0, MPI_COMM_WORLD);
+      OK(mamr_nccl_init(G, id), "nccl_init");
+      nccl_moves = !(getenv("MAMR_HOST_MIGRATION") && atoi(getenv("MAMR_HOST_MIGRATION")));
+   }
    stage_tile = (double *) malloc((size_t)num_vars*tile_doubles()*sizeof(double));
    memset(&seen, 0, sizeof seen);
 }
@@ -159,10 +174,18 @@ static void sync_topology(void)
    topo_dirty = 0;
 }
 
+/* staged block payloads (pack_block/unpack_block below) move now: every rank gets
+ * here at the same point of the program */
+static void flush_moves(void)
+{
+   if (G && nccl_moves) OK(mamr_flush_block_moves(G), "flush_block_moves");
+}
+
 static void ready(void)
 {
    ensure_ctx();
    upload_host_blocks();
+   flush_moves();
    sync_topology();
 }
 
@@ -233,9 +256,18 @@ double check_sum(int var)
 }
 
 /* pack_block/unpack_block: 50 int slots of header exactly as the receiver's
- * unpack expects them (pack.c:43-65), then the interiors var-major from the
- * device (pack.c:66-70).  The message still travels through send_buff/recv_buff
- * and the host MPI of rcb.c:207-337. */
+ * unpack expects them (pack.c:43-65); the payload (pack.c:66-70: interiors
+ * var-major, from double index 50) follows one of two routes.
+ *   one rank, or MAMR_HOST_MIGRATION=1: through send_buff/recv_buff and the host
+ *     MPI of rcb.c:237,261 (mamr_pack_block / mamr_unpack_block);
+ *   N ranks (default): GPU to GPU.  exchange() (rcb.c:207-337) always sends a block
+ *     to blocks[n].new_proc (rcb.c:249-253), so pack_block() stages the payload for
+ *     that rank on the device and writes its own rank where the payload would
+ *     start; unpack_block() reads the source rank there and stages the receive.
+ *     The staged moves run as one NCCL group when move_blocks()/load_balance()
+ *     return (wrapped below), at the same program point on every rank.  The host
+ *     message keeps its reference size (block_size, rcb.c:214); only its first 51
+ *     doubles are meaningful. */
 static int *hdr_fields(block *bp, int *h, int unpack)
 {
    int i, j, k, *f[5];
@@ -259,14 +291,19 @@ void pack_block(int n)
    block *bp = &blocks[n];
    long long *ll = (long long *) send_buff;
    int *end;
-   ready();
+   ensure_ctx();
+   upload_host_blocks();
    ll[0] = (long long) bp->number;
    ll[1] = (bp->parent_node == my_pe && bp->parent != -1) ? (long long)(-2 - bp->parent)
                                                           : (long long) bp->parent;
    ll[2] = (long long) bp->num_prime;
    end = hdr_fields(bp, (int *) send_buff + 6, 0);
    /* the payload starts at double index (number of int slots used): pack.c:66 */
-   OK(mamr_pack_block(G, n, send_buff + (end - (int *) send_buff)), "pack_block");
+   if (nccl_moves) {
+      send_buff[end - (int *) send_buff] = (double) my_pe;
+      OK(mamr_stage_send_block(G, n, bp->new_proc), "stage_send_block");
+   } else
+      OK(mamr_pack_block(G, n, send_buff + (end - (int *) send_buff)), "pack_block");
 }
 
 void unpack_block(int n)
@@ -274,13 +311,17 @@ void unpack_block(int n)
    block *bp = &blocks[n];
    long long *ll = (long long *) recv_buff;
    int *end;
-   ready();
+   ensure_ctx();
+   upload_host_blocks();
    bp->new_proc = -1;
    bp->number = (num_sz) ll[0];
    bp->parent = (num_sz) ll[1];
    bp->num_prime = (num_sz) ll[2];
    end = hdr_fields(bp, (int *) recv_buff + 6, 1);
-   OK(mamr_unpack_block(G, n, recv_buff + (end - (int *) recv_buff)), "unpack_block");
+   if (nccl_moves)
+      OK(mamr_stage_recv_block(G, n, (int) recv_buff[end - (int *) recv_buff]), "stage_recv_block");
+   else
+      OK(mamr_unpack_block(G, n, recv_buff + (end - (int *) recv_buff)), "unpack_block");
    topo_dirty = 1;
 }
 
@@ -300,6 +341,29 @@ void __real_refine(int ts);
 void __wrap_refine(int ts)
 {
    __real_refine(ts);
+   topo_dirty = 1;
+}
+
+/* block migration: the staged payloads move when the host has finished its
+ * handshakes (load_balance() -> rcb()/sfc() -> move_blocks(), rcb.c:36-54,191,830;
+ * redistribute_blocks() -> move_blocks(), refine.c:706).  ld --wrap redirects the
+ * calls that cross object files, which covers every path into exchange(). */
+void __real_load_balance(void);
+void __wrap_load_balance(void)
+{
+   __real_load_balance();
+   flush_moves();
+   topo_dirty = 1;
+}
+
+void __real_move_blocks(double *tp, double *tm, double *tu);
+void __wrap_move_blocks(double *tp, double *tm, double *tu)
+{
+   double t1;
+   __real_move_blocks(tp, tm, tu);
+   t1 = timer();
+   flush_moves();
+   *tm += timer() - t1;
    topo_dirty = 1;
 }
 

@@ -62,7 +62,9 @@ EXPORTS = [
     "mamr_comm", "mamr_stencil_driver", "mamr_stencil_calc", "mamr_stencil_vars",
     "mamr_check_sum", "mamr_check_sum_vars", "mamr_stage", "mamr_split_block",
     "mamr_consolidate_block", "mamr_pack_block", "mamr_unpack_block", "mamr_send_block",
-    "mamr_recv_block", "mamr_nccl_get_unique_id", "mamr_nccl_init", "mamr_timer_begin",
+    "mamr_recv_block", "mamr_stage_send_block", "mamr_stage_recv_block", "mamr_flush_block_moves",
+    "mamr_pending_block_moves", "mamr_device_count",
+    "mamr_nccl_get_unique_id", "mamr_nccl_init", "mamr_timer_begin",
     "mamr_timer_end", "mamr_kernel_timing", "mamr_kernel_time_ms",
     "mamr_plan_create", "mamr_plan_phase_dir", "mamr_plan_num_ops", "mamr_plan_get_ops",
     "mamr_plan_block_begin", "mamr_plan_destroy",
@@ -327,6 +329,19 @@ class DeviceMesh:
 
     def recv_block(self, slot, src):
         self._ck(self.L.mamr_recv_block(self.h, int(slot), int(src)))
+
+    # staged form (what integration/glue.c uses under exchange(), rcb.c:207-337)
+    def stage_send_block(self, slot, dest):
+        self._ck(self.L.mamr_stage_send_block(self.h, int(slot), int(dest)))
+
+    def stage_recv_block(self, slot, src):
+        self._ck(self.L.mamr_stage_recv_block(self.h, int(slot), int(src)))
+
+    def flush_block_moves(self):
+        self._ck(self.L.mamr_flush_block_moves(self.h))
+
+    def pending_block_moves(self):
+        return int(self.L.mamr_pending_block_moves(self.h))
 
     def sync(self):
         self._ck(self.L.mamr_sync(self.h))

@@ -181,6 +181,12 @@ struct mamr_ctx {
    int rops_cap = 4096, rops_pos = 0;
    double *d_payload = nullptr;
    double *h_stage = nullptr;   // pinned, one block
+   // staged block migration (mamr_stage_send_block / _recv_block / mamr_flush_block_moves):
+   // payloads packed at stage time, exchanged later in ONE NCCL group
+   struct MoveRec { int slot, peer; };
+   std::vector<MoveRec> mv_send, mv_recv;
+   double *d_mv_send = nullptr, *d_mv_recv = nullptr;
+   size_t mv_send_cap = 0, mv_recv_cap = 0;     // in blocks
 
    mamr_counters cnt;
 
@@ -1126,6 +1132,8 @@ void mamr_destroy(mamr_ctx *c)
    if (c->h_sums) cudaFreeHost(c->h_sums);
    cudaFree(c->d_rops);
    cudaFree(c->d_payload);
+   cudaFree(c->d_mv_send);
+   cudaFree(c->d_mv_recv);
    if (c->h_stage) cudaFreeHost(c->h_stage);
    if (c->ev_begin) cudaEventDestroy(c->ev_begin);
    if (c->ev_end) cudaEventDestroy(c->ev_end);
@@ -1642,6 +1650,109 @@ int mamr_recv_block(mamr_ctx *c, int slot, int src_rank)
    CU(cudaGetLastError());
    touch_all(c);
    return MAMR_OK;
+}
+
+// ---- staged migration -------------------------------------------------------
+// The reference moves blocks one at a time through a blocking pairwise handshake
+// (rcb.c:207-337).  Issuing one ncclSend/ncclRecv per pack_block()/unpack_block()
+// at those call sites can deadlock on the device (two ranks that each send before
+// they receive), so the drop-in splits the move: the sender packs the payload into
+// a staging area when the host says so (the slot is reused right afterwards,
+// rcb.c:259-266), the receiver only records (slot, source), and every rank later
+// calls mamr_flush_block_moves() at the same point of the program -- one NCCL
+// group holding all sends and receives, then the unpack kernels.  Per pair of
+// ranks the k-th staged send matches the k-th staged receive.
+namespace {
+int grow_stage(mamr_ctx *c, double **buf, size_t *cap, size_t need, size_t keep)
+{
+   if (need <= *cap) return MAMR_OK;
+   const size_t n = (size_t)c->p.num_vars*c->p.nx*c->p.ny*c->p.nz;
+   size_t ncap = *cap ? *cap : 16;
+   while (ncap < need) ncap *= 2;
+   double *nb = nullptr;
+   CU(cudaMalloc(&nb, ncap*n*sizeof(double)));
+   if (*buf && keep)
+      CU(cudaMemcpyAsync(nb, *buf, keep*n*sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   if (*buf) CU(cudaFree(*buf));
+   *buf = nb;
+   *cap = ncap;
+   return MAMR_OK;
+}
+}  // namespace
+
+int mamr_stage_send_block(mamr_ctx *c, int slot, int dest_rank)
+{
+   CK(check_slot(c, slot));
+   if (!c->nccl) return fail(MAMR_ENCCL, "stage_send_block: mamr_nccl_init was not called");
+   if (dest_rank < 0 || dest_rank >= c->p.num_ranks || dest_rank == c->p.rank)
+      return fail(MAMR_EINVAL, "stage_send_block: bad destination rank %d", dest_rank);
+   for (const mamr_ctx::MoveRec &r : c->mv_recv)
+      if (r.slot == slot)
+         return fail(MAMR_EINVAL, "stage_send_block: slot %d still waits for its own payload", slot);
+   CK(flush_pending(c));
+   const size_t n = (size_t)c->p.num_vars*c->p.nx*c->p.ny*c->p.nz;
+   CK(grow_stage(c, &c->d_mv_send, &c->mv_send_cap, c->mv_send.size() + 1, c->mv_send.size()));
+   double *dst = c->d_mv_send + c->mv_send.size()*n;
+   for (const Run &r : runs_of(c, 0, c->p.num_vars, false)) {
+      launch_pack_block(vpool(c, r.start), c->g, slot, r.start, r.num, dst, c->stream);
+      c->cnt.kernel_launches++;
+   }
+   CU(cudaGetLastError());
+   c->mv_send.push_back({ slot, dest_rank });
+   return MAMR_OK;
+}
+
+int mamr_stage_recv_block(mamr_ctx *c, int slot, int src_rank)
+{
+   CK(check_slot(c, slot));
+   if (!c->nccl) return fail(MAMR_ENCCL, "stage_recv_block: mamr_nccl_init was not called");
+   if (src_rank < 0 || src_rank >= c->p.num_ranks || src_rank == c->p.rank)
+      return fail(MAMR_EINVAL, "stage_recv_block: bad source rank %d", src_rank);
+   for (const mamr_ctx::MoveRec &r : c->mv_recv)
+      if (r.slot == slot)
+         return fail(MAMR_EINVAL, "stage_recv_block: slot %d already waits for a payload", slot);
+   c->mv_recv.push_back({ slot, src_rank });
+   return MAMR_OK;
+}
+
+int mamr_pending_block_moves(mamr_ctx *c)
+{
+   return c ? (int)(c->mv_send.size() + c->mv_recv.size()) : 0;
+}
+
+int mamr_flush_block_moves(mamr_ctx *c)
+{
+   if (!c) return fail(MAMR_EINVAL, "null context");
+   if (c->mv_send.empty() && c->mv_recv.empty()) return MAMR_OK;
+   if (!c->nccl) return fail(MAMR_ENCCL, "flush_block_moves: mamr_nccl_init was not called");
+   CK(settle_all(c));
+   const size_t n = (size_t)c->p.num_vars*c->p.nx*c->p.ny*c->p.nz;
+   CK(grow_stage(c, &c->d_mv_recv, &c->mv_recv_cap, c->mv_recv.size(), 0));
+   NC(g_nccl.GroupStart());
+   for (size_t i = 0; i < c->mv_send.size(); i++)
+      NC(g_nccl.Send(c->d_mv_send + i*n, n, NCCL_DOUBLE, c->mv_send[i].peer, c->nccl, c->stream));
+   for (size_t i = 0; i < c->mv_recv.size(); i++)
+      NC(g_nccl.Recv(c->d_mv_recv + i*n, n, NCCL_DOUBLE, c->mv_recv[i].peer, c->nccl, c->stream));
+   NC(g_nccl.GroupEnd());
+   for (size_t i = 0; i < c->mv_recv.size(); i++)
+      for (const Run &r : runs_of(c, 0, c->p.num_vars, false)) {
+         launch_unpack_block(vpool(c, r.start), c->g, c->mv_recv[i].slot, r.start, r.num,
+                             c->d_mv_recv + i*n, c->stream);
+         c->cnt.kernel_launches++;
+      }
+   CU(cudaGetLastError());
+   c->cnt.migrate_bytes += (double)c->mv_send.size()*n*sizeof(double);
+   if (!c->mv_recv.empty()) touch_all(c);
+   c->mv_send.clear();
+   c->mv_recv.clear();
+   return MAMR_OK;
+}
+
+int mamr_device_count(void)
+{
+   int n = 0;
+   return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
 }
 
 // ---- multi-GPU -------------------------------------------------------------

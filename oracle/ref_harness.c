@@ -249,3 +249,41 @@ void refh_unpack_face(double *buf, int slot, int face_case, int dir, int start, 
 /* glibc rand() state is process-wide; reseed to the default (1) so that every
  * instance reproduces the reference's never-seeded sequence (init.c:490-494) */
 void refh_reseed(void) { srand(1); }
+
+/* ---- off-rank comm lists (comm.h:38-55) and the message exchange of one
+ *      direction (comm.c:71-84,120-151), for the multi-rank planner tests ---- */
+
+/* what: 0 partner, 1 index, 2 num, 3 send_size, 4 recv_size (per partner);
+ *       5 block, 6 face_case, 7 send_off, 8 recv_off (per face).
+ * Returns the element count; copies when out != NULL. */
+int refh_get_comm_list(int dir, int what, int *out)
+{
+   int *src[9], n, i;
+   src[0] = comm_partner[dir]; src[1] = comm_index[dir]; src[2] = comm_num[dir];
+   src[3] = send_size[dir]; src[4] = recv_size[dir]; src[5] = comm_block[dir];
+   src[6] = comm_face_case[dir]; src[7] = comm_send_off[dir]; src[8] = comm_recv_off[dir];
+   n = what < 5 ? num_comm_partners[dir] : num_cases[dir];
+   if (out)
+      for (i = 0; i < n; i++)
+         out[i] = src[what][i];
+   return n;
+}
+
+/* one message per partner of direction `dir`, from `send` into `recv` (both laid
+ * out like send_buff/recv_buff: partner message at the offset of its first face) */
+void refh_exchange_dir(int dir, const double *send, double *recv)
+{
+   int i, np = num_comm_partners[dir];
+   MPI_Request *rq = (MPI_Request *) malloc((size_t)(2*np + 1)*sizeof(MPI_Request));
+   for (i = 0; i < np; i++)
+      MPI_Irecv(recv + comm_recv_off[dir][comm_index[dir][i]], recv_size[dir][i], MPI_DOUBLE,
+                comm_partner[dir][i], 900 + dir, MPI_COMM_WORLD, &rq[i]);
+   for (i = 0; i < np; i++)
+      MPI_Isend((void *)(send + comm_send_off[dir][comm_index[dir][i]]), send_size[dir][i], MPI_DOUBLE,
+                comm_partner[dir][i], 900 + dir, MPI_COMM_WORLD, &rq[np + i]);
+   for (i = 0; i < 2*np; i++)
+      MPI_Wait(&rq[i], MPI_STATUS_IGNORE);
+   free(rq);
+}
+
+void refh_barrier(void) { MPI_Barrier(MPI_COMM_WORLD); }

@@ -31,9 +31,11 @@ P_NAMES = ["nx", "ny", "nz", "num_vars", "comm_vars", "max_blocks", "stencil",
 
 def lib_path(variant: str) -> str:
     """"ref" / "omp": the unmodified reference; "int": the same host code linked
-    against the CUDA stage path through integration/glue.c."""
-    if variant == "int":
-        return os.path.join(INT_DIR, "libminiamr_int.so")
+    against the CUDA stage path through integration/glue.c.  "ref_mp" / "int_mp":
+    the same two linked with the multi-process minimpi back-end (one instance per
+    rank, started by minimpi/_bin/minimpirun: tests/mp_worker.py)."""
+    if variant in ("int", "int_mp"):
+        return os.path.join(INT_DIR, f"libminiamr_{variant}.so")
     return os.path.join(REF_DIR, f"libminiamr_{variant}.so")
 
 
@@ -49,7 +51,7 @@ class RefMiniAMR:
         src = lib_path(variant)
         if not os.path.exists(src):
             raise FileNotFoundError(f"{src} missing: run `make -C oracle` / `make -C integration`")
-        if variant == "int":
+        if variant in ("int", "int_mp"):
             # the private copy below cannot use its $ORIGIN-relative rpath: make the
             # CUDA library resident first, the copy then binds to it by soname
             C.CDLL(os.path.join(os.path.dirname(HERE), "miniamr_b200", "libminiamr_b200.so"),
@@ -211,6 +213,28 @@ class RefMiniAMR:
         buf = (C.c_int * 9)()
         self.lib.refh_get_counters(buf)
         return dict(same=list(buf[0:3]), diff=list(buf[3:6]), bc=list(buf[6:9]))
+
+    def comm_lists(self):
+        """the off-rank comm lists of comm.h:38-55 as the `dirs` argument of
+        miniamr_b200.capi (three dicts of int32 arrays)"""
+        names = ["partner", "index", "num", "send_size", "recv_size", "block", "face_case",
+                 "send_off", "recv_off"]
+        dirs = []
+        for d in range(3):
+            D = {}
+            for w, k in enumerate(names):
+                n = self.lib.refh_get_comm_list(d, w, None)
+                a = np.zeros(max(n, 1), np.int32)
+                self.lib.refh_get_comm_list(d, w, a.ctypes.data_as(C.POINTER(C.c_int)))
+                D[k] = a[:n].copy()
+            dirs.append(D)
+        return dirs
+
+    def exchange_dir(self, d: int, send: np.ndarray, recv: np.ndarray):
+        """one message per partner of direction d over the host MPI (comm.c:71-84,120-151)"""
+        assert send.dtype == np.float64 and recv.dtype == np.float64
+        self.lib.refh_exchange_dir(int(d), send.ctypes.data_as(C.c_void_p),
+                                   recv.ctypes.data_as(C.c_void_p))
 
     def global_active(self) -> int:
         return int(self.lib.refh_global_active())

@@ -1,0 +1,95 @@
+"""The drop-in at N ranks: the UNMODIFIED reference host code on every rank
+(refine, RCB/SFC load balancing, comm-list maintenance, parent/refine exchanges
+over the host channel minimpi) with the CUDA stage path underneath — one rank
+per GPU, ghost faces and migrated block payloads over NCCL — against the
+unmodified reference run at the same N ranks on the CPU.  Same command line,
+same partition, same rand() fill per rank: every block must end on the same
+rank, at the same level, with bit-identical data.  Needs >= 2 GPUs
+(`gpurun --gpus 2`)."""
+import numpy as np
+import pytest
+
+from mputil import MPIRUN, defined_mask, run_ranks
+from oracle import refharness
+import os
+
+pytestmark = pytest.mark.gpu
+
+
+def ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+MOVING = "--num_objects 1 --object 2 0 0.2 0.2 0.2 0.09 0.07 0.05 0.2 0.2 0.2 0 0 0"
+TWO = ("--num_objects 2 --object 2 0 0.2 0.2 0.2 0.09 0.07 0.05 0.2 0.2 0.2 0 0 0 "
+       "--object 0 0 0.5 0.5 0.9 0 0 -0.08 0.6 0.6 0.02 0 0 0")
+RUNS = {
+    # refine + coarsen every step, RCB after every refine: blocks migrate
+    "amr7_rcb": (2, f"--npx 2 --init_x 1 --init_y 2 --init_z 2 --nx 4 --ny 4 --nz 4 --num_vars 4 --comm_vars 3 "
+                    f"--num_refine 3 --block_change 1 --max_blocks 3000 --refine_freq 1 --num_tsteps 6 "
+                    f"--stages_per_ts 4 --checksum_freq 2 --lb_opt 1 {MOVING}"),
+    # configs[3] in small: sphere + slab, 10^3 blocks, load balance in every refine phase
+    "amr7_two_objects": (2, f"--npy 2 --init_x 2 --init_y 1 --init_z 2 --nx 10 --ny 10 --nz 10 --num_vars 3 "
+                            f"--num_refine 3 --max_blocks 4000 --refine_freq 2 --num_tsteps 4 --stages_per_ts 5 "
+                            f"--lb_opt 2 {TWO}"),
+    # Morton SFC partitioner instead of RCB
+    "amr7_morton": (2, f"--npz 2 --init_x 2 --init_y 2 --init_z 1 --nx 6 --ny 4 --nz 8 --num_vars 2 --num_refine 2 "
+                       f"--max_blocks 2000 --refine_freq 1 --num_tsteps 4 --stages_per_ts 3 --morton --permute "
+                       f"{MOVING}"),
+    # configs[4] in small: staged ghost comm, 27-point, checksum every stage
+    "uni27_staged": (2, "--npx 2 --init_x 1 --init_y 2 --init_z 2 --nx 10 --ny 10 --nz 10 --num_vars 7 "
+                        "--comm_vars 3 --stencil 27 --uniform_refine 1 --num_refine 1 --max_blocks 200 "
+                        "--num_tsteps 2 --stages_per_ts 4 --checksum_freq 1"),
+}
+
+
+def compare(name, ref, dev, args):
+    p = dict(zip(refharness.P_NAMES, ref["params"]))
+    assert dev["global_active"] == ref["global_active"] == len(dev["blocks"]) == len(ref["blocks"])
+    assert sorted(dev["blocks"]) == sorted(ref["blocks"])
+    defined = defined_mask(p["nx"], p["ny"], p["nz"], p["stencil"])[None]
+    ranks = set()
+    for num, (rank, level, data) in ref["blocks"].items():
+        drank, dlevel, ddata = dev["blocks"][num]
+        assert (drank, dlevel) == (rank, level), f"{name}: block {num}"
+        bad = (data.view(np.uint64) != ddata.view(np.uint64)) & defined
+        assert not bad.any(), f"{name}: block {num} on rank {rank}: {int(bad.sum())} cells differ, first {np.argwhere(bad)[0]}"
+        ranks.add(rank)
+    assert len(ranks) > 1
+    assert np.all(np.abs(ref["sums"] - dev["sums"]) <= 1e-13*np.abs(ref["sums"]))
+    for a, b in zip(ref["per_rank"], dev["per_rank"]):
+        assert a["rank"] == b["rank"] and a["n"] == b["n"]
+        assert (a["counters"] == b["counters"]).all()        # same/diff/bc faces feed profile.c
+        assert a["fp_adds"] == b["fp_adds"]
+
+
+needs = pytest.mark.skipif(not (os.path.exists(MPIRUN) and refharness.available("ref_mp") and
+                                refharness.available("int_mp")),
+                           reason="minimpi/_bin, oracle/_ref or integration/_bin not built")
+
+
+@needs
+@pytest.mark.parametrize("name", sorted(RUNS))
+def test_n_rank_run_matches_reference(name):
+    n, args = RUNS[name]
+    if ngpus() < n:
+        pytest.skip(f"needs {n} GPUs")
+    ref = run_ranks("ref_mp", n, args.split())
+    dev = run_ranks("int_mp", n, args.split())
+    compare(name, ref, dev, args)
+
+
+@needs
+def test_host_channel_migration_gives_the_same_result():
+    """MAMR_HOST_MIGRATION=1: block payloads through send_buff and the host MPI
+    (the reference's own route) instead of NCCL"""
+    n, args = RUNS["amr7_rcb"]
+    if ngpus() < n:
+        pytest.skip(f"needs {n} GPUs")
+    ref = run_ranks("ref_mp", n, args.split())
+    dev = run_ranks("int_mp", n, args.split(), env={"MAMR_HOST_MIGRATION": "1"})
+    compare("amr7_rcb/host", ref, dev, args)

@@ -54,6 +54,16 @@ def bytes_per_update(n, stencil):
     return dict(stage=16 + 24*h, stencil=16 + 8*h, ghost=16*h)
 
 
+def kernel_name(n, stencil):
+    """the kernel api.cu:flush_pending launches for this block size on a uniform mesh"""
+    if stencil == 7 and n == 32:
+        return "slab7_kernel<32> (streamed halo gather + 7-pt stencil through a TMA plane ring; slab7.cu)"
+    if n in (8, 10, 12, 16):
+        return (f"fused2_kernel<{stencil},{n},elide> (halo gather + stencil, ghost stores elided, "
+                "Z faces from the export pool; fused2.cu)")
+    return f"fused_kernel<{stencil}> (halo gather + stencil; fused.cu)"
+
+
 def rank_grid(n):
     return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n]
 
@@ -332,8 +342,11 @@ def run_ours(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else \
             "fallback (B200_PROFILING.md 6.65 TB/s)"
-        st_launch_ms = kt["stencil_ms"]/max(1, kt["stencil_launches"])
-        st_bytes = bpu["stencil"]*nblocks*n**3*V          # per launch, this rank
+        # one stage = the fused kernel over every block and variable of this rank (one
+        # launch; two -- interior blocks, then boundary blocks -- when an off-rank
+        # exchange overlaps the first): device time of those launches per stage
+        st_launch_ms = kt["stencil_ms"]/max(1, args.steps)
+        st_bytes = bpu["stencil"]*nblocks*n**3*V          # per stage, this rank
         achieved = st_bytes/(st_launch_ms*1e-3)/1e9
         traffic = None
         try:
@@ -353,9 +366,8 @@ def run_ours(args):
                        "bytes_per_gpu": d.pool_bytes(),
                        "cache": "inputs (7.6 GB/GPU at the default size) exceed the 126 MB L2"},
             "roofline": {"bound": "hbm",
-                         "kernel": (f"fused2_kernel<{stencil},{n},elide> (halo gather + stencil, "
-                                    "ghost stores elided, Z faces from the export pool)" if n == 16 else
-                                    f"fused_kernel<{stencil}> (halo gather + stencil)"),
+                         "kernel": kernel_name(n, stencil),
+                         "launches_per_step": kt["stencil_launches"]/max(1, args.steps),
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved/peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": st_bytes,

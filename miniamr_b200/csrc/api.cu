@@ -148,6 +148,18 @@ struct mamr_ctx {
    BoxOp *d_hops[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
    int *d_hbegin[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
    cudaStream_t stream = nullptr;
+   // Overlap of the off-rank exchange with the stencil of the blocks that do not read
+   // it (MAMR_NO_OVERLAP=1 turns it off): pack kernels + NCCL run on `xstream`; the
+   // fused kernel is launched for the interior blocks on the main stream right away
+   // and for the boundary blocks on `bstream`, which waits for the exchange (ev_xchg).
+   // order_ord[ord] = interior blocks, then boundary blocks (each in processing order).
+   cudaStream_t xstream = nullptr, bstream = nullptr;
+   cudaEvent_t ev_data = nullptr, ev_xchg = nullptr, ev_pre = nullptr, ev_bdone = nullptr;
+   bool use_overlap = true;
+   bool xchg_pending = false;
+   int *d_order_ord[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+   int n_interior[6] = {0, 0, 0, 0, 0, 0};
+   std::vector<int> h_order;
 
    int num_active = 0;
    std::vector<mamr_block> blocks;
@@ -165,8 +177,18 @@ struct mamr_ctx {
 
    DirLists cl[3];
    bool have_partners = false;
-   double *d_send[3] = {nullptr, nullptr, nullptr}, *d_recv[3] = {nullptr, nullptr, nullptr};
+   // One send buffer per direction.  Receive buffers come in `nsets` sets, one per
+   // group of comm_vars variables (driver.c:75-89 calls comm() once per group and
+   // stage): the messages of a group stay valid until the same group's next comm(),
+   // so deferred exchanges and elided ghost layers of the OTHER groups need not be
+   // made real when a buffer is reused.  pc_set / stale_set: the set a variable's
+   // deferred comm() / stale ghost layer reads.
+   static constexpr int MAX_SETS = 16;
+   int nsets = 1;
+   double *d_send[3] = {nullptr, nullptr, nullptr};
+   double *d_recvs[MAX_SETS][3] = {};
    size_t send_cap[3] = {0, 0, 0}, recv_cap[3] = {0, 0, 0};
+   std::vector<unsigned char> pc_set, stale_set;
 
    double *d_partials = nullptr;
    size_t partials_cap = 0;
@@ -237,7 +259,8 @@ struct KTimer {
    mamr_ctx *c;
    EventPair ep;
    bool on;
-   KTimer(mamr_ctx *c_, int cls) : c(c_), on(c_->ktiming)
+   cudaStream_t st;
+   KTimer(mamr_ctx *c_, int cls, cudaStream_t st_ = nullptr) : c(c_), on(c_->ktiming), st(st_ ? st_ : c_->stream)
    {
       if (!on) return;
       for (cudaEvent_t *e : { &ep.a, &ep.b }) {
@@ -248,12 +271,12 @@ struct KTimer {
             cudaEventCreate(e);
       }
       ep.cls = cls;
-      cudaEventRecord(ep.a, c->stream);
+      cudaEventRecord(ep.a, st);
    }
    ~KTimer()
    {
       if (!on) return;
-      cudaEventRecord(ep.b, c->stream);
+      cudaEventRecord(ep.b, st);
       c->kev.push_back(ep);
    }
 };
@@ -539,9 +562,11 @@ int build_ops(mamr_ctx *c)
          c->send_cap[d] = smax;
       }
       if (rmax > c->recv_cap[d]) {
-         if (c->d_recv[d]) CU(cudaFree(c->d_recv[d]));
-         CU(cudaMalloc(&c->d_recv[d], rmax*sizeof(double)));
-         CU(cudaMemsetAsync(c->d_recv[d], 0, rmax*sizeof(double), c->stream));
+         for (int q = 0; q < c->nsets; q++) {
+            if (c->d_recvs[q][d]) CU(cudaFree(c->d_recvs[q][d]));
+            CU(cudaMalloc(&c->d_recvs[q][d], rmax*sizeof(double)));
+            CU(cudaMemsetAsync(c->d_recvs[q][d], 0, rmax*sizeof(double), c->stream));
+         }
          c->recv_cap[d] = rmax;
       }
    }
@@ -575,16 +600,26 @@ int build_ops(mamr_ctx *c)
    return MAMR_OK;
 }
 
+// the main stream is about to touch the message buffers: an exchange still in
+// flight on the exchange stream comes first
+int wait_xchg(mamr_ctx *c)
+{
+   if (!c->xchg_pending) return MAMR_OK;
+   CU(cudaStreamWaitEvent(c->stream, c->ev_xchg, 0));
+   c->xchg_pending = false;
+   return MAMR_OK;
+}
+
 // one message per (direction, partner), comm.c:71-84 / 120-151, as NCCL send/recv
-int exchange_dir(mamr_ctx *c, int d)
+int exchange_dir(mamr_ctx *c, int d, cudaStream_t st, int set)
 {
    const DirLists &L = c->cl[d];
    NC(g_nccl.GroupStart());
    for (size_t i = 0; i < L.partner.size(); i++) {
-      NC(g_nccl.Recv(c->d_recv[d] + L.recv_off[L.index[i]], (size_t)L.recv_size[i], NCCL_DOUBLE,
-                     L.partner[i], c->nccl, c->stream));
+      NC(g_nccl.Recv(c->d_recvs[set][d] + L.recv_off[L.index[i]], (size_t)L.recv_size[i], NCCL_DOUBLE,
+                     L.partner[i], c->nccl, st));
       NC(g_nccl.Send(c->d_send[d] + L.send_off[L.index[i]], (size_t)L.send_size[i], NCCL_DOUBLE,
-                     L.partner[i], c->nccl, c->stream));
+                     L.partner[i], c->nccl, st));
       c->cnt.counter_halo_recv[d]++;
       c->cnt.counter_halo_send[d]++;
       c->cnt.size_mesg_recv[d] += (double)L.recv_size[i]*sizeof(double);
@@ -600,11 +635,12 @@ int exchange_dir(mamr_ctx *c, int d)
 // their current pool (all in the same pool): the split path.  buf_var0 is the
 // first variable of the comm() call (variable 0 of the message buffers); with
 // exchange == false the receive buffers already hold this call's messages.
-int comm_split(mamr_ctx *c, int start, int num, int ord, int buf_var0, bool exchange)
+int comm_split(mamr_ctx *c, int start, int num, int ord, int buf_var0, bool exchange, int set)
 {
    if (c->ops_dirty) CK(build_ops(c));
    if (c->have_partners && !c->nccl)
       return fail(MAMR_ENCCL, "comm: off-rank partners present but mamr_nccl_init was not called");
+   CK(wait_xchg(c));
    double *pool = vpool(c, start);
    for (int o = 0; o < 3; o++) {
       const int d = kPerm[ord][o];
@@ -612,15 +648,15 @@ int comm_split(mamr_ctx *c, int start, int num, int ord, int buf_var0, bool exch
       if (!c->ops_main[d].empty() && num > 0) {
          KTimer t(c, KC_GHOST);
          launch_ghost(c->d_ops + c->off_main[d], (int)c->ops_main[d].size(), pool, c->d_send[d],
-                      c->d_recv[d], c->g.var_stride, start, num, buf_var0, c->stream);
+                      c->d_recvs[set][d], c->g.var_stride, start, num, buf_var0, c->stream);
          c->cnt.kernel_launches++;
       }
       if (!L.partner.empty()) {
-         if (exchange) CK(exchange_dir(c, d));
+         if (exchange) CK(exchange_dir(c, d, c->stream, set));
          if (!c->ops_unpack[d].empty() && num > 0) {
             KTimer t(c, KC_GHOST);
             launch_ghost(c->d_ops + c->off_unpack[d], (int)c->ops_unpack[d].size(), pool,
-                         c->d_send[d], c->d_recv[d], c->g.var_stride, start, num, buf_var0,
+                         c->d_send[d], c->d_recvs[set][d], c->g.var_stride, start, num, buf_var0,
                          c->stream);
             c->cnt.kernel_launches++;
          }
@@ -637,8 +673,32 @@ int materialize_comm(mamr_ctx *c, int v0, int n)
    for (const Run &r : runs_of(c, v0, n, true)) {
       const int ord = c->pc_ord[r.start];
       if (ord < 0) continue;
-      CK(comm_split(c, r.start, r.num, ord, c->pc_start[r.start], false));
+      CK(comm_split(c, r.start, r.num, ord, c->pc_start[r.start], false, c->pc_set[r.start]));
       for (int v = r.start; v < r.start + r.num; v++) c->pc_ord[v] = -1;
+   }
+   return MAMR_OK;
+}
+
+int regen_ghosts(mamr_ctx *c, int v0, int n);
+
+// receive-buffer set `set` is about to be overwritten: deferred exchanges and stale
+// ghost layers that still read it become real (maximal runs of variables)
+int release_recv_set(mamr_ctx *c, int set)
+{
+   const int V = c->p.num_vars;
+   for (int v = 0; v < V;) {
+      if (!(c->pc_ord[v] >= 0 && c->pc_set[v] == set)) { v++; continue; }
+      int e = v;
+      while (e < V && c->pc_ord[e] >= 0 && c->pc_set[e] == set) e++;
+      CK(materialize_comm(c, v, e - v));
+      v = e;
+   }
+   for (int v = 0; v < V;) {
+      if (!(c->stale[v] && c->stale_set[v] == set)) { v++; continue; }
+      int e = v;
+      while (e < V && c->stale[e] && c->stale_set[e] == set) e++;
+      CK(regen_ghosts(c, v, e - v));
+      v = e;
    }
    return MAMR_OK;
 }
@@ -685,6 +745,17 @@ int build_slab_plan(mamr_ctx *c, int ord)
             if (f < 4) { fsrc[6*a + f] = op.src_base - 1 - PL; continue; }
             if (sc == cell(1, 1, 1) || sc == cell(1, 1, N)) {
                fsrc[6*a + f] = m*2LL*N*N + (sc == cell(1, 1, 1) ? 0 : (long long)N*N);
+               continue;
+            }
+         }
+         // a whole same-level face out of a receive buffer is a compact N x N plane per
+         // variable there (pack_face order, comm.c:266-270): bulk-copied as well.  The
+         // buffer index travels in the top byte of the offset.
+         if (f >= 0 && op.src_mem >= BM_BUF0 && op.src_mem < BM_BUF0 + 3 && op.src_vs == (long long)N*N &&
+             op.src_base%2 == 0 && op.src_base < (1LL << 48)) {
+            const int d = f/2, sa = d == 0 ? 1 : 0, fa = d == 2 ? 1 : 2;
+            if (op.src_str[sa] == N && op.src_str[fa] == 1) {
+               fsrc[6*a + f] = op.src_base | ((long long)(op.src_mem - BM_BUF0 + 1) << 56);
                continue;
             }
          }
@@ -798,6 +869,26 @@ int ensure_plan(mamr_ctx *c, int ord)
       CU(cudaStreamSynchronize(c->stream));   // the host vectors go out of scope
    }
    CK(build_slab_plan(c, ord));
+   // interior blocks (no halo cell out of a receive buffer) first, boundary blocks last
+   if (c->d_order_ord[ord]) CU(cudaFree(c->d_order_ord[ord]));
+   c->d_order_ord[ord] = nullptr;
+   c->n_interior[ord] = 0;
+   if (c->have_partners && c->use_overlap && c->num_active > 0 &&
+       (int)c->h_order.size() == c->num_active) {
+      std::vector<char> bnd(c->num_active, 0);
+      for (size_t a = 0; a + 1 < P.begin.size(); a++)
+         for (int o = P.begin[a]; o < P.begin[a + 1]; o++)
+            if (P.ops[o].src_mem != BM_POOL) { bnd[a] = 1; break; }
+      std::vector<int> ordv;
+      ordv.reserve(c->num_active);
+      for (int a : c->h_order) if (!bnd[a]) ordv.push_back(a);
+      c->n_interior[ord] = (int)ordv.size();
+      for (int a : c->h_order) if (bnd[a]) ordv.push_back(a);
+      CU(cudaMalloc(&c->d_order_ord[ord], ordv.size()*sizeof(int)));
+      CU(cudaMemcpyAsync(c->d_order_ord[ord], ordv.data(), ordv.size()*sizeof(int),
+                         cudaMemcpyHostToDevice, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+   }
    for (int o = 0; o < 3; o++) {
       if (c->d_pack[ord][o]) CU(cudaFree(c->d_pack[ord][o]));
       c->d_pack[ord][o] = nullptr;
@@ -827,6 +918,8 @@ int fused_ready(mamr_ctx *c, int ord, bool *yes)
 int regen_ghosts(mamr_ctx *c, int v0, int n)
 {
    int v = v0;
+   for (int u = v0; u < v0 + n; u++)
+      if (c->stale[u]) { CK(wait_xchg(c)); break; }
    while (v < v0 + n) {
       if (!c->stale[v]) { v++; continue; }
       int e = v + 1;
@@ -838,7 +931,8 @@ int regen_ghosts(mamr_ctx *c, int v0, int n)
          return fail(MAMR_EINVAL, "internal: halo plan of an elided stage is gone");
       if (c->num_active > 0) {
          KTimer t(c, KC_GHOST);
-         const double *recv[3] = { c->d_recv[0], c->d_recv[1], c->d_recv[2] };
+         double *const *rs = c->d_recvs[c->stale_set[v]];
+         const double *recv[3] = { rs[0], rs[1], rs[2] };
          launch_halo_fill(c->d_hops[ord], c->d_hbegin[ord], c->d_slots, c->num_active, c->pool[in],
                           c->pool[in ^ 1], c->g, recv, v, e - v, c->stale_start[v], false, c->stream);
          c->cnt.kernel_launches++;
@@ -861,7 +955,8 @@ int flush_pending(mamr_ctx *c)
       const int in = c->cur[r.start];
       if (ord >= 0) {
          // comm() + stencil in one pass: current pool -> other pool
-         const double *recv[3] = { c->d_recv[0], c->d_recv[1], c->d_recv[2] };
+         double *const *rs = c->d_recvs[c->pc_set[r.start]];
+         const double *recv[3] = { rs[0], rs[1], rs[2] };
          const bool slab = c->slab_ok[ord];
          const bool f2 = c->fused2_geom && c->use_fused2;
          const bool elide = slab || (f2 && c->use_elide && c->plan[ord].elidable && c->d_lops[ord]);
@@ -870,6 +965,7 @@ int flush_pending(mamr_ctx *c)
             bool synced = true;
             for (int v = r.start; v < r.start + r.num; v++) synced = synced && c->shell_synced[v];
             if (!synced) {
+               CK(wait_xchg(c));
                KTimer t(c, KC_GHOST);
                launch_halo_fill(c->d_hops[ord], c->d_hbegin[ord], c->d_slots, c->num_active,
                                 c->pool[in], c->pool[in ^ 1], c->g, recv, r.start, r.num,
@@ -891,32 +987,55 @@ int flush_pending(mamr_ctx *c)
                v = e;
             }
          }
-         {
-            KTimer t(c, KC_STENCIL);
+         auto launch = [&](const int *order, int count, cudaStream_t st) {
+            if (count <= 0) return;
             if (slab)
-               launch_slab7(c->pool[in], c->pool[in ^ 1], c->g, c->d_slots, c->d_order,
-                            c->num_active, c->d_fsrc[ord], c->d_cops[ord], c->d_cbegin[ord], recv,
-                            r.start, r.num, c->pc_start[r.start], c->zf[in], c->zf[in ^ 1],
-                            c->stream);
+               launch_slab7(c->pool[in], c->pool[in ^ 1], c->g, c->d_slots, order,
+                            count, c->d_fsrc[ord], c->d_cops[ord], c->d_cbegin[ord], recv,
+                            r.start, r.num, c->pc_start[r.start], c->zf[in], c->zf[in ^ 1], st);
             else if (f2)
-               launch_fused2(c->pool[in], c->pool[in ^ 1], c->g, c->d_slots, c->d_order,
-                             c->num_active, elide ? c->d_lops[ord] : c->d_hops[ord],
+               launch_fused2(c->pool[in], c->pool[in ^ 1], c->g, c->d_slots, order,
+                             count, elide ? c->d_lops[ord] : c->d_hops[ord],
                              elide ? c->d_lbegin[ord] : c->d_hbegin[ord], recv, r.start, r.num,
                              c->pc_start[r.start], c->p.stencil, elide, c->zf[in], c->zf[in ^ 1],
-                             c->d_zsrc[ord], c->stream);
+                             c->d_zsrc[ord], st);
             else
-               launch_fused(c->pool[in], c->pool[in ^ 1], c->g, c->d_slots, c->d_order,
-                            c->num_active, c->d_hops[ord], c->d_hbegin[ord], recv, r.start, r.num,
-                            c->pc_start[r.start], c->p.stencil, c->stream);
+               launch_fused(c->pool[in], c->pool[in ^ 1], c->g, c->d_slots, order,
+                            count, c->d_hops[ord], c->d_hbegin[ord], recv, r.start, r.num,
+                            c->pc_start[r.start], c->p.stencil, st);
+            c->cnt.kernel_launches++;
+         };
+         if (c->xchg_pending && c->d_order_ord[ord] && c->n_interior[ord] > 0 &&
+             c->n_interior[ord] < c->num_active) {
+            // The exchange is still in flight.  Interior blocks do not need it: they
+            // start now on the main stream.  The boundary blocks go to a second stream
+            // that waits for the exchange only, so their CTAs fill the machine as the
+            // interior launch drains instead of waiting for its tail (both launches
+            // read the same pool and write disjoint tiles).  One timed interval.
+            KTimer t(c, KC_STENCIL);
+            CU(cudaEventRecord(c->ev_pre, c->stream));
+            launch(c->d_order_ord[ord], c->n_interior[ord], c->stream);
+            CU(cudaStreamWaitEvent(c->bstream, c->ev_pre, 0));
+            CU(cudaStreamWaitEvent(c->bstream, c->ev_xchg, 0));
+            launch(c->d_order_ord[ord] + c->n_interior[ord], c->num_active - c->n_interior[ord],
+                   c->bstream);
+            CU(cudaEventRecord(c->ev_bdone, c->bstream));
+            CU(cudaStreamWaitEvent(c->stream, c->ev_bdone, 0));
+            CU(cudaStreamWaitEvent(c->stream, c->ev_xchg, 0));
+            c->xchg_pending = false;
+         } else {
+            CK(wait_xchg(c));
+            KTimer t(c, KC_STENCIL);
+            launch(c->d_order, c->num_active, c->stream);
          }
          if (c->num_active > 0) {
-            c->cnt.kernel_launches++;
             for (int v = r.start; v < r.start + r.num; v++) {
                c->cur[v] ^= 1;
                c->stale[v] = elide ? 1 : 0;
                c->zf_ok[v] = elide ? 1 : 0;
                c->stale_ord[v] = (signed char)ord;
                c->stale_start[v] = c->pc_start[r.start];
+               c->stale_set[v] = c->pc_set[r.start];
                if (elide) c->shell_synced[v] = 1;
             }
          }
@@ -1052,6 +1171,9 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
    c->stale_start.assign(p.num_vars, 0);
    c->shell_synced.assign(p.num_vars, 0);
    c->zf_ok.assign(p.num_vars, 0);
+   c->pc_set.assign(p.num_vars, 0);
+   c->stale_set.assign(p.num_vars, 0);
+   c->nsets = std::min<int>(mamr_ctx::MAX_SETS, (p.num_vars + c->comm_vars - 1)/c->comm_vars);
    std::string err, why;
    if (!stencil_configure(g, err) || !fused_configure(g, err) || !fused2_configure(g, err) ||
        !slab7_configure(g, err)) {
@@ -1093,6 +1215,19 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
    CUC(cudaMalloc(&c->d_rops, c->rops_cap*sizeof(RefineOp)));
    CUC(cudaMalloc(&c->d_payload, (size_t)p.num_vars*p.nx*p.ny*p.nz*sizeof(double)));
    CUC(cudaMallocHost(&c->h_stage, (size_t)p.num_vars*g.tile*sizeof(double)));
+   {
+      // exchange stream: highest priority, so that its pack/NCCL CTAs are placed as
+      // soon as CTAs of the interior stencil kernel retire
+      int lo = 0, hi = 0;
+      CUC(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CUC(cudaStreamCreateWithPriority(&c->xstream, cudaStreamNonBlocking, hi));
+   }
+   CUC(cudaEventCreateWithFlags(&c->ev_data, cudaEventDisableTiming));
+   CUC(cudaEventCreateWithFlags(&c->ev_xchg, cudaEventDisableTiming));
+   CUC(cudaStreamCreateWithFlags(&c->bstream, cudaStreamNonBlocking));
+   CUC(cudaEventCreateWithFlags(&c->ev_pre, cudaEventDisableTiming));
+   CUC(cudaEventCreateWithFlags(&c->ev_bdone, cudaEventDisableTiming));
+   { const char *no = getenv("MAMR_NO_OVERLAP"); c->use_overlap = !(no && no[0] == '1'); }
    CUC(cudaEventCreate(&c->ev_begin));
    CUC(cudaEventCreate(&c->ev_end));
    CUC(cudaStreamSynchronize(c->stream));
@@ -1104,6 +1239,8 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
 void mamr_destroy(mamr_ctx *c)
 {
    if (!c) return;
+   if (c->xstream) cudaStreamSynchronize(c->xstream);
+   if (c->bstream) cudaStreamSynchronize(c->bstream);
    if (c->stream) cudaStreamSynchronize(c->stream);
    drain_ktimers(c);
    for (cudaEvent_t e : c->ev_free) cudaEventDestroy(e);
@@ -1126,7 +1263,10 @@ void mamr_destroy(mamr_ctx *c)
    cudaFree(c->d_slots);
    cudaFree(c->d_order);
    cudaFree(c->d_ops);
-   for (int d = 0; d < 3; d++) { cudaFree(c->d_send[d]); cudaFree(c->d_recv[d]); }
+   for (int d = 0; d < 3; d++) {
+      cudaFree(c->d_send[d]);
+      for (int q = 0; q < mamr_ctx::MAX_SETS; q++) cudaFree(c->d_recvs[q][d]);
+   }
    cudaFree(c->d_partials);
    cudaFree(c->d_sums);
    if (c->h_sums) cudaFreeHost(c->h_sums);
@@ -1135,6 +1275,13 @@ void mamr_destroy(mamr_ctx *c)
    cudaFree(c->d_mv_send);
    cudaFree(c->d_mv_recv);
    if (c->h_stage) cudaFreeHost(c->h_stage);
+   for (int o = 0; o < 6; o++) cudaFree(c->d_order_ord[o]);
+   if (c->ev_data) cudaEventDestroy(c->ev_data);
+   if (c->ev_xchg) cudaEventDestroy(c->ev_xchg);
+   if (c->ev_pre) cudaEventDestroy(c->ev_pre);
+   if (c->ev_bdone) cudaEventDestroy(c->ev_bdone);
+   if (c->xstream) cudaStreamDestroy(c->xstream);
+   if (c->bstream) cudaStreamDestroy(c->bstream);
    if (c->ev_begin) cudaEventDestroy(c->ev_begin);
    if (c->ev_end) cudaEventDestroy(c->ev_end);
    if (c->stream) cudaStreamDestroy(c->stream);
@@ -1145,6 +1292,7 @@ int mamr_sync(mamr_ctx *c)
 {
    if (!c) return fail(MAMR_EINVAL, "null context");
    CK(settle_all(c));
+   CK(wait_xchg(c));
    CU(cudaStreamSynchronize(c->stream));
    return MAMR_OK;
 }
@@ -1327,6 +1475,7 @@ int mamr_set_topology(mamr_ctx *c, int num_active, const mamr_block *sorted_bloc
    for (int a = 0; a < num_active; a++) slots[a] = sorted_blocks[a].slot;
    CU(cudaStreamSynchronize(c->stream));
    const std::vector<int> order = processing_order(c);
+   c->h_order = order;
    if (num_active) {
       CU(cudaMemcpyAsync(c->d_slots, slots.data(), num_active*sizeof(int),
                          cudaMemcpyHostToDevice, c->stream));
@@ -1385,6 +1534,7 @@ int mamr_comm(mamr_ctx *c, int start, int num_comm, int stage)
    CK(settle_data(c, start, num_comm));
    if (c->ops_dirty) CK(build_ops(c));   // also validates the topology (comm.c:198-201)
    const int ord = order_index(c, stage);
+   const int set = (start/c->comm_vars)%c->nsets;
    bool defer = false;
    CK(fused_ready(c, ord, &defer));
    // Ghost cells an eliding launch left stale: this exchange overwrites every ghost
@@ -1398,35 +1548,50 @@ int mamr_comm(mamr_ctx *c, int start, int num_comm, int stage)
       // the fused kernel performs this exchange when the stencil of the variables
       // is launched; anything else that needs the ghost cells materialises it
       if (c->have_partners && num_comm > 0) {
-         // the message buffers are about to be reused: an older deferred comm()
-         // that still needs them becomes real first
-         CK(materialize_comm(c, 0, c->p.num_vars));
-         CK(regen_ghosts(c, 0, c->p.num_vars));   // they may need the old messages
+         // this group's receive buffers are about to be reused: whatever else still
+         // reads them (another group mapped to the same set) becomes real first
+         CK(release_recv_set(c, set));
          // off-rank faces: per phase, fill the send buffers from resolved origins
          // (pack_face, comm.c:254-401) and exchange them (comm.c:71-84, 120-151)
          double *send[3] = { c->d_send[0], c->d_send[1], c->d_send[2] };
-         const double *recv[3] = { c->d_recv[0], c->d_recv[1], c->d_recv[2] };
+         const double *recv[3] = { c->d_recvs[set][0], c->d_recvs[set][1], c->d_recvs[set][2] };
+         CK(wait_xchg(c));
+         cudaStream_t xs = c->stream;
+         if (c->use_overlap) {
+            // the exchange reads the variables as the main stream leaves them now and
+            // reuses buffers the main stream may still be reading
+            xs = c->xstream;
+            CU(cudaEventRecord(c->ev_data, c->stream));
+            CU(cudaStreamWaitEvent(xs, c->ev_data, 0));
+         }
          for (int o = 0; o < 3; o++) {
             const int d = kPerm[ord][o];
             if (c->cl[d].partner.empty()) continue;
             for (const Run &r : runs_of(c, start, num_comm, false)) {
-               KTimer t(c, KC_GHOST);
+               KTimer t(c, KC_GHOST, xs);
                launch_boxops(c->d_pack[ord][o], (int)c->pack[ord][o].size(), vpool(c, r.start),
                              vpool(c, r.start), c->g.var_stride, send, recv, r.start, r.num, start,
-                             c->stream);
+                             xs);
                c->cnt.kernel_launches++;
             }
-            CK(exchange_dir(c, d));
+            CK(exchange_dir(c, d, xs, set));
+         }
+         if (c->use_overlap) {
+            CU(cudaEventRecord(c->ev_xchg, xs));
+            c->xchg_pending = true;
          }
          CU(cudaGetLastError());
       }
       for (int v = start; v < start + num_comm; v++) {
          c->pc_ord[v] = (signed char)ord;
          c->pc_start[v] = start;
+         c->pc_set[v] = (unsigned char)set;
       }
-   } else
+   } else {
+      if (c->have_partners && num_comm > 0) CK(release_recv_set(c, set));
       for (const Run &r : runs_of(c, start, num_comm, false))
-         CK(comm_split(c, r.start, r.num, ord, start, true));
+         CK(comm_split(c, r.start, r.num, ord, start, true, set));
+   }
    for (int d = 0; d < 3; d++) {
       c->cnt.counter_same[d] += c->n_same[d];
       c->cnt.counter_diff[d] += c->n_diff[d];

@@ -127,11 +127,22 @@ slab7_kernel(const SlabArgs B)
    if (tid >= CT) {
       // ------------------------------ copy warp ------------------------------
       if (tid != CT) return;
+      // per face: offset (or -1) and where it points: 0 = the pool / Z-face pool,
+      // 1..3 = receive buffer of direction 0..2 (a compact N x N plane per variable)
       long long fs[6];
+      int fm[6];
 #pragma unroll
-      for (int f = 0; f < 6; f++) fs[f] = B.fsrc[6*a + f];
+      for (int f = 0; f < 6; f++) {
+         const long long w = B.fsrc[6*a + f];
+         fm[f] = w >= 0 ? (int)(w >> 56) : 0;
+         fs[f] = w >= 0 ? (w & ((1LL << 56) - 1)) : w;
+      }
+      auto rbuf = [&](int f, int v) {
+         const double *r = fm[f] == 1 ? A.recv[0] : (fm[f] == 2 ? A.recv[1] : A.recv[2]);
+         return r + (long long)(v - A.buf_var0)*(N*N) + fs[f];
+      };
       constexpr uint32_t ROWS_BYTES = (uint32_t)N*SJ*8u, ROW_BYTES = (uint32_t)SJ*8u,
-                         ZROW_BYTES = (uint32_t)N*8u;
+                         ZROW_BYTES = (uint32_t)N*8u, FACE_BYTES = (uint32_t)N*N*8u;
       auto load_plane = [&](int g) {
          const int t = g/NP, p = g - t*NP;
          const int v = v0 + t;
@@ -140,7 +151,12 @@ slab7_kernel(const SlabArgs B)
          const double *pin = A.pool_in + (long long)v*A.var_stride;
          if (p == 0 || p == NP - 1) {
             const long long src = p ? fs[1] : fs[0];
-            if (src >= 0) {
+            const int mem = p ? fm[1] : fm[0];
+            if (src >= 0 && mem) {
+               // off-rank X face: the compact plane lands behind row 0 (read through offX)
+               mbar_arrive_expect_tx(bar, FACE_BYTES);
+               bulk_g2s(dst + SJ, p ? rbuf(1, v) : rbuf(0, v), FACE_BYTES, bar);
+            } else if (src >= 0) {
                mbar_arrive_expect_tx(bar, ROWS_BYTES);
                bulk_g2s(dst + SJ, pin + src, ROWS_BYTES, bar);
             } else
@@ -148,17 +164,28 @@ slab7_kernel(const SlabArgs B)
             return;
          }
          uint32_t bytes = ROWS_BYTES;
-         if (fs[2] >= 0) bytes += ROW_BYTES;
-         if (fs[3] >= 0) bytes += ROW_BYTES;
+         if (fs[2] >= 0) bytes += fm[2] ? ZROW_BYTES : ROW_BYTES;
+         if (fs[3] >= 0) bytes += fm[3] ? ZROW_BYTES : ROW_BYTES;
          if (fs[4] >= 0) bytes += ZROW_BYTES;
          if (fs[5] >= 0) bytes += ZROW_BYTES;
          mbar_arrive_expect_tx(bar, bytes);
          bulk_g2s(dst + SJ, pin + slot_off + (long long)p*PL + SJ, ROWS_BYTES, bar);
-         if (fs[2] >= 0) bulk_g2s(dst, pin + fs[2] + (long long)p*PL, ROW_BYTES, bar);
-         if (fs[3] >= 0) bulk_g2s(dst + (N + 1)*SJ, pin + fs[3] + (long long)p*PL, ROW_BYTES, bar);
+         // Y halo rows: the neighbour's padded row, or (off rank) row p of the compact
+         // plane in the receive buffer, which lands one cell to the left (offS / offN)
+         if (fs[2] >= 0) {
+            if (fm[2]) bulk_g2s(dst, rbuf(2, v) + (long long)(p - 1)*N, ZROW_BYTES, bar);
+            else bulk_g2s(dst, pin + fs[2] + (long long)p*PL, ROW_BYTES, bar);
+         }
+         if (fs[3] >= 0) {
+            if (fm[3]) bulk_g2s(dst + (N + 1)*SJ, rbuf(3, v) + (long long)(p - 1)*N, ZROW_BYTES, bar);
+            else bulk_g2s(dst + (N + 1)*SJ, pin + fs[3] + (long long)p*PL, ROW_BYTES, bar);
+         }
          const double *zin = A.zf_in + (long long)v*A.zf_var_stride;
-         if (fs[4] >= 0) bulk_g2s(dst + PL, zin + fs[4] + (long long)(p - 1)*N, ZROW_BYTES, bar);
-         if (fs[5] >= 0) bulk_g2s(dst + PL + N, zin + fs[5] + (long long)(p - 1)*N, ZROW_BYTES, bar);
+         if (fs[4] >= 0)
+            bulk_g2s(dst + PL, (fm[4] ? rbuf(4, v) : zin + fs[4]) + (long long)(p - 1)*N, ZROW_BYTES, bar);
+         if (fs[5] >= 0)
+            bulk_g2s(dst + PL + N, (fm[5] ? rbuf(5, v) : zin + fs[5]) + (long long)(p - 1)*N, ZROW_BYTES,
+                     bar);
       };
       int next = 0;                      // next plane to load
       for (; next < R && next < total_planes; next++) load_plane(next);
@@ -231,7 +258,15 @@ slab7_kernel(const SlabArgs B)
       s7_cp_async_commit();
    }
 
-   int offC[S::CPT], offD[S::CPT], offU[S::CPT], offO[S::CPT];
+   // faces that arrive as compact planes out of a receive buffer (see the copy warp)
+   bool fbuf[4];
+#pragma unroll
+   for (int f = 0; f < 4; f++) {
+      const long long w = B.fsrc[6*a + f];
+      fbuf[f] = w >= 0 && (w >> 56) != 0;
+   }
+   int offC[S::CPT], offD[S::CPT], offU[S::CPT], offO[S::CPT], offS[S::CPT], offN[S::CPT],
+       offX[S::CPT];
    bool live[S::CPT];
 #pragma unroll
    for (int q = 0; q < S::CPT; q++) {
@@ -242,6 +277,9 @@ slab7_kernel(const SlabArgs B)
       offC[q] = j*SJ + k;
       offD[q] = k > 1 ? offC[q] - 1 : PL + (j - 1);
       offU[q] = k < N ? offC[q] + 1 : PL + N + (j - 1);
+      offS[q] = (j == 1 && fbuf[2]) ? k - 1 : offC[q] - SJ;
+      offN[q] = (j == N && fbuf[3]) ? (N + 1)*SJ + k - 1 : offC[q] + SJ;
+      offX[q] = SJ + (j - 1)*N + (k - 1);
       offO[q] = (j - 1)*SJ + k;
    }
 
@@ -260,21 +298,22 @@ slab7_kernel(const SlabArgs B)
          const double *p0 = ring + (size_t)((g - 1)%R)*S::SLOT, *p1 = ring + (size_t)(g%R)*S::SLOT;
 #pragma unroll
          for (int q = 0; q < S::CPT; q++) {
-            prev[q] = p0[offC[q]];
+            prev[q] = p0[fbuf[0] ? offX[q] : offC[q]];
             cur[q] = p1[offC[q]];
          }
       }
       mbar_wait(&full[(g + 1)%R], (uint32_t)(((g + 1)/R) & 1));
       const double *pc = ring + (size_t)(g%R)*S::SLOT, *pn = ring + (size_t)((g + 1)%R)*S::SLOT;
       double r[S::CPT];
+      const bool east_buf = fbuf[1] && i == N;
 #pragma unroll
       for (int q = 0; q < S::CPT; q++) {
-         const double e = pn[offC[q]];
-         double x = prev[q] + pc[offC[q] - SJ];      // W + S
+         const double e = pn[east_buf ? offX[q] : offC[q]];
+         double x = prev[q] + pc[offS[q]];           // W + S
          x += pc[offD[q]];                           // + D
          x += cur[q];                                // + C
          x += pc[offU[q]];                           // + U
-         x += pc[offC[q] + SJ];                      // + N
+         x += pc[offN[q]];                           // + N
          x += e;                                     // + E
          r[q] = x;
          prev[q] = cur[q];

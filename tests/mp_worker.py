@@ -21,7 +21,9 @@ def main():
     variant, outdir, args = sys.argv[1], sys.argv[2], sys.argv[3:]
     r = refharness.RefMiniAMR(args, variant=variant, run_driver=True)
     p = r.p
-    r.comm(0, p["num_vars"], 0)
+    cv = p["comm_vars"] if 0 < p["comm_vars"] <= p["num_vars"] else p["num_vars"]
+    for start in range(0, p["num_vars"], cv):      # message buffers hold comm_vars variables
+        r.comm(start, min(cv, p["num_vars"] - start), 0)
     r.sync_host()
     slots = r.sorted_slots()
     numbers = np.zeros(len(slots), np.int64)

@@ -40,6 +40,8 @@ WORKLOADS = {
                  desc="BASELINE configs[2]: uniform 32^3-cell blocks, 40 vars, 7-pt"),
     "cfg1u": dict(n=10, num_vars=40, stencil=7, bpd=16,
                   desc="10^3-cell blocks, 40 vars, 7-pt (configs[0] shape, uniform mesh)"),
+    "cfg5": dict(n=10, num_vars=160, stencil=27, bpd=12, comm_vars=40,
+                 desc="BASELINE configs[4] shape: 10^3-cell blocks, 160 vars in 4 comm groups of 40, 27-pt"),
 }
 
 
@@ -147,7 +149,7 @@ def cpu_reference(workload, steps, warmup, budget_s=None):
     n, V = w["n"], w["num_vars"]
     R = 3 if n <= 16 else 2                   # 512 or 64 blocks: seconds per stage at most
     nblocks = 8**R
-    args = (f"--nx {n} --ny {n} --nz {n} --num_vars {V} --stencil {w['stencil']} "
+    args = (f"--nx {n} --ny {n} --nz {n} --num_vars {V} --comm_vars {w.get('comm_vars', 0)} --stencil {w['stencil']} "
             f"--uniform_refine 1 --num_refine {R} --max_blocks {nblocks + 16}").split()
     r = refharness.RefMiniAMR(args, variant=variant)
     r.init()
@@ -228,8 +230,9 @@ def run_ours(args):
     B = args.blocks or w["bpd"]
     nblocks = B**3
     npx, npy, npz = rank_grid(world)
-    top = uniform_mesh(B, B, B, npx, npy, npz, rank, n, n, n, comm_vars=V, stencil=stencil)
-    d = DeviceMesh(n, n, n, V, nblocks, stencil=stencil, device=local, rank=rank,
+    cv = w.get("comm_vars", V)
+    top = uniform_mesh(B, B, B, npx, npy, npz, rank, n, n, n, comm_vars=cv, stencil=stencil)
+    d = DeviceMesh(n, n, n, V, nblocks, stencil=stencil, comm_vars=cv, device=local, rank=rank,
                    num_ranks=world)
     d.set_topology(top["slots"], top["level"], top["nei_level"], top["nei"])
     if world > 1:
@@ -310,9 +313,10 @@ def run_ours(args):
         for st in range(steps):
             if reupload_every_step:
                 d.upload_vars(0, V, nblocks, host.data_ptr())
-            d.comm(0, V, st)
-            for v in range(V):
-                d.stencil_driver(v, st)
+            for start in range(0, V, cv):                    # driver.c:75-89
+                d.comm(start, min(cv, V - start), st)
+                for v in range(start, min(start + cv, V)):
+                    d.stencil_driver(v, st)
             for v in range(V):
                 d.check_sum(v)
         ms_ = d.timer_end()
@@ -361,7 +365,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic (uniform random interiors, seed 1234+rank)",
             "config": {"workload": f"{args.workload}: {w['desc']}",
-                       "blocks_per_gpu": nblocks, "cells_per_block": n**3, "num_vars": V,
+                       "blocks_per_gpu": nblocks, "cells_per_block": n**3, "num_vars": V, "comm_vars": cv,
                        "stencil": stencil, "rank_grid": [npx, npy, npz],
                        "bytes_per_gpu": d.pool_bytes(),
                        "cache": "inputs (7.6 GB/GPU at the default size) exceed the 126 MB L2"},

@@ -44,7 +44,8 @@ typedef struct {
    int max_blocks;      /* --max_blocks: pool slots on this rank                 */
    int stencil;         /* --stencil: 7 or 27 (0, the variable-work mix, is not
                            on this path yet -> MAMR_EUNSUPPORTED)                */
-   int code;            /* --code: 0 (1 and 2 -> MAMR_EUNSUPPORTED)              */
+   int code;            /* --code 0|1|2: all run the code-0 exchange (same result
+                           on every cell the stencil reads)        */
    int permute;         /* --permute (comm.c:45-55)                              */
    int device;          /* CUDA device ordinal, -1 = current device              */
    int rank, num_ranks; /* my_pe, num_pes: one process per GPU                   */

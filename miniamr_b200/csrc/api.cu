@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "common.cuh"
@@ -1078,11 +1079,10 @@ int check_slot(mamr_ctx *c, int slot)
    return MAMR_OK;
 }
 
-// Order in which the fused kernel visits the blocks.  A Z face is the expensive
-// part of a tile's halo (k is the fastest axis: one 8-byte cell per 32-byte
-// sector), so blocks are visited in +z chains: the tile a CTA pulls its Z halo
-// from is then the tile the neighbouring CTA streams through L2 at about the
-// same time.  Chains start in sorted_list order, which keeps x neighbours close.
+// Order in which the fused kernel visits the blocks: neighbouring blocks should be
+// in flight at about the same time, so that a halo row pulled from a neighbour tile
+// and that tile's own load share one trip from DRAM.  (MAMR_ORDER=zchain is the
+// older order: +z chains started in sorted_list order.)
 std::vector<int> processing_order(const mamr_ctx *c)
 {
    const int nb = c->num_active;
@@ -1096,6 +1096,58 @@ std::vector<int> processing_order(const mamr_ctx *c)
       return (m >= 0 && m < c->p.max_blocks) ? slot2idx[m] : -1;
    };
    order.reserve(nb);
+   // Default: bricks of 4 x 4 x 4 blocks, z fastest inside a brick.  Integer coordinates
+   // come from the same-level face links (one origin per connected same-level region).
+   // x, y AND z neighbours are then visited within a few hundred CTAs of each other, i.e.
+   // while their rows are still in L2: 2.60 -> 2.53 ms on cfg2 (z-chains only keep x and z
+   // neighbours close; y halo rows had left the L2).  MAMR_ORDER=zchain | brick:bx,by,bz.
+   int bx = 4, by = 4, bz = 4;
+   if (const char *e = getenv("MAMR_ORDER")) {
+      if (!strcmp(e, "zchain")) bx = 0;
+      else if (sscanf(e, "brick:%d,%d,%d", &bx, &by, &bz) != 3 || bx < 1 || by < 1 || bz < 1)
+         bx = by = bz = 4;
+   }
+   if (bx > 0 && nb > 0) {
+      std::vector<int> cx(nb, 0), cy(nb, 0), cz(nb, 0), comp(nb, -1), stack;
+      int ncomp = 0;
+      for (int a0 = 0; a0 < nb; a0++) {
+         if (comp[a0] >= 0) continue;
+         comp[a0] = ncomp;
+         stack.push_back(a0);
+         while (!stack.empty()) {
+            const int a = stack.back();
+            stack.pop_back();
+            for (int l = 0; l < 6; l++) {
+               const int m = link(a, l);
+               if (m < 0 || comp[m] >= 0) continue;
+               comp[m] = ncomp;
+               cx[m] = cx[a] + (l == 0 ? -1 : (l == 1 ? 1 : 0));
+               cy[m] = cy[a] + (l == 2 ? -1 : (l == 3 ? 1 : 0));
+               cz[m] = cz[a] + (l == 4 ? -1 : (l == 5 ? 1 : 0));
+               stack.push_back(m);
+            }
+         }
+         ncomp++;
+      }
+      std::vector<int> mnx(ncomp, 1 << 30), mny(ncomp, 1 << 30), mnz(ncomp, 1 << 30);
+      for (int a = 0; a < nb; a++) {
+         mnx[comp[a]] = std::min(mnx[comp[a]], cx[a]);
+         mny[comp[a]] = std::min(mny[comp[a]], cy[a]);
+         mnz[comp[a]] = std::min(mnz[comp[a]], cz[a]);
+      }
+      struct Key { int comp, Bz, By, Bx, y, x, z, a; };
+      std::vector<Key> keys(nb);
+      for (int a = 0; a < nb; a++) {
+         const int x = cx[a] - mnx[comp[a]], y = cy[a] - mny[comp[a]], z = cz[a] - mnz[comp[a]];
+         keys[a] = { comp[a], z/bz, y/by, x/bx, y%by, x%bx, z%bz, a };
+      }
+      std::sort(keys.begin(), keys.end(), [](const Key &p, const Key &q) {
+         return std::tie(p.comp, p.Bz, p.By, p.Bx, p.y, p.x, p.z, p.a) <
+                std::tie(q.comp, q.Bz, q.By, q.Bx, q.y, q.x, q.z, q.a);
+      });
+      for (const Key &k : keys) order.push_back(k.a);
+      return order;
+   }
    for (int a0 = 0; a0 < nb; a0++) {
       if (done[a0]) continue;
       int a = a0;
@@ -1140,8 +1192,14 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
    if (p.max_blocks <= 0) return fail(MAMR_EINVAL, "max_blocks must be > 0");
    if (p.stencil != 7 && p.stencil != 27)
       return fail(MAMR_EUNSUPPORTED, "--stencil %d: only 7 and 27 are on the device path", p.stencil);
-   if (p.code != 0)
-      return fail(MAMR_EUNSUPPORTED, "--code %d: only the minimal-send mode 0 is on the device path", p.code);
+   // --code 1|2 ("send ghosts", "... and process on send", comm.c:403-989,1152-1461) change
+   // what travels in a message and where the restriction runs, not what the exchange
+   // delivers: in the reference itself every cell the stencil reads ends up bit-identical
+   // to --code 0 (tests/test_plan_multi_rank.py).  The device path therefore runs its
+   // code-0 exchange for all three; the host's comm lists keep their (larger) code-1/2
+   // offsets and each face uses the front of its slot.
+   if (p.code < 0 || p.code > 2)
+      return fail(MAMR_EINVAL, "--code %d: must be 0, 1 or 2 (main.c:157)", p.code);
    if (p.num_ranks < 1 || p.rank < 0 || p.rank >= p.num_ranks)
       return fail(MAMR_EINVAL, "bad rank %d of %d", p.rank, p.num_ranks);
    int ndev = 0;

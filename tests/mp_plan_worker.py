@@ -42,6 +42,12 @@ def main():
             r_ = max(r_, int(D["recv_off"][f0]) + int(D["recv_size"][i]))
         ssize.append(s)
         rsize.append(r_)
+    # --code 1|2: the reference additionally writes ghost edges/corners the 7-point
+    # stencil never reads; everything the stencil reads must still agree
+    mask = np.ones((nx + 2, ny + 2, nz + 2), bool)
+    if p["code"] != 0 and p["stencil"] == 7:
+        from mputil import defined_mask
+        mask = defined_mask(nx, ny, nz, 7)
     cells = 0
     for st in range(stages):
         plan = HaloPlan(nx, ny, nz, V, p["max_blocks"], slots, level, nei_level, nei, dirs=dirs,
@@ -63,7 +69,7 @@ def main():
             r.comm(start, num, st)                            # the reference's own exchange
             for s in slots:
                 want = r.get_slot(int(s))
-                bad = got[s, start:start + num].view(np.uint64) != want[start:start + num].view(np.uint64)
+                bad = (got[s, start:start + num].view(np.uint64) != want[start:start + num].view(np.uint64)) & mask[None]
                 assert not bad.any(), (f"rank {p['my_pe']} stage {st} vars {start}+{num} slot {s}: "
                                        f"{int(bad.sum())} cells differ, first {np.argwhere(bad)[0]}")
                 cells += bad.size

@@ -44,6 +44,23 @@ RUNS = {
     "uni27_staged": (2, "--npx 2 --init_x 1 --init_y 2 --init_z 2 --nx 10 --ny 10 --nz 10 --num_vars 7 "
                         "--comm_vars 3 --stencil 27 --uniform_refine 1 --num_refine 1 --max_blocks 200 "
                         "--num_tsteps 2 --stages_per_ts 4 --checksum_freq 1"),
+    # message modes: --code 1|2, --send_faces, --blocking_send
+    "amr7_code1_send_faces": (2, f"--npx 2 --init_x 1 --init_y 2 --init_z 2 --nx 4 --ny 6 --nz 4 --num_vars 3 "
+                                 f"--comm_vars 2 --num_refine 3 --max_blocks 3000 --refine_freq 1 --num_tsteps 4 "
+                                 f"--stages_per_ts 3 --lb_opt 1 --code 1 --send_faces {MOVING}"),
+    "uni27_code2_blocking": (2, "--npz 2 --init_x 2 --init_y 2 --init_z 1 --nx 4 --ny 4 --nz 6 --num_vars 4 "
+                                "--comm_vars 3 --stencil 27 --uniform_refine 1 --num_refine 1 --max_blocks 200 "
+                                "--num_tsteps 2 --stages_per_ts 3 --checksum_freq 1 --code 2 --blocking_send"),
+    # 4 and 8 ranks (skipped on smaller boxes): configs[3] in small at the rank grid the north star names
+    "amr7_two_objects_4": (4, f"--npx 2 --npy 2 --init_x 1 --init_y 1 --init_z 2 --nx 8 --ny 8 --nz 8 --num_vars 3 "
+                              f"--num_refine 3 --max_blocks 4000 --refine_freq 2 --num_tsteps 4 --stages_per_ts 4 "
+                              f"--lb_opt 1 {TWO}"),
+    "amr7_two_objects_8": (8, f"--npx 2 --npy 2 --npz 2 --init_x 1 --init_y 1 --init_z 1 --nx 10 --ny 10 --nz 10 "
+                              f"--num_vars 4 --num_refine 4 --max_blocks 4000 --refine_freq 2 --num_tsteps 4 "
+                              f"--stages_per_ts 5 --lb_opt 1 {TWO}"),
+    "uni27_staged_8": (8, "--npx 2 --npy 2 --npz 2 --init_x 1 --init_y 1 --init_z 1 --nx 10 --ny 10 --nz 10 "
+                          "--num_vars 8 --comm_vars 3 --stencil 27 --uniform_refine 1 --num_refine 2 "
+                          "--max_blocks 200 --num_tsteps 2 --stages_per_ts 4 --checksum_freq 1"),
 }
 
 

@@ -30,6 +30,17 @@ CASES = {
     "amr7_hilbert_permute_4": (4, 6, f"--npx 2 --npy 2 --init_x 1 --init_y 1 --init_z 2 --nx 4 --ny 4 --nz 6 "
                                      f"--num_vars 2 --num_refine 2 --max_blocks 2000 --refine_freq 1 "
                                      f"--num_tsteps 3 --stages_per_ts 2 --hilbert --permute {MOVING}"),
+    # message modes: --send_faces / --blocking_send change the transport only; --code 1|2 also
+    # what a message holds -- the cells the stencil reads must not change
+    "amr7_code1_sendfaces_4": (4, 2, f"--npx 2 --npy 2 --init_x 1 --init_y 1 --init_z 2 --nx 4 --ny 6 --nz 4 "
+                                     f"--num_vars 3 --comm_vars 2 --num_refine 3 --max_blocks 3000 --refine_freq 1 "
+                                     f"--num_tsteps 3 --stages_per_ts 2 --lb_opt 1 --code 1 --send_faces {MOVING}"),
+    "amr7_code2_blocking_2": (2, 2, f"--npz 2 --init_x 2 --init_y 2 --init_z 1 --nx 4 --ny 4 --nz 4 --num_vars 2 "
+                                    f"--num_refine 2 --max_blocks 2000 --refine_freq 1 --num_tsteps 3 "
+                                    f"--stages_per_ts 2 --code 2 --blocking_send {MOVING}"),
+    "uni27_code1_2": (2, 2, "--npy 2 --init_x 2 --init_y 1 --init_z 1 --nx 4 --ny 4 --nz 6 --num_vars 3 "
+                            "--stencil 27 --uniform_refine 1 --num_refine 1 --max_blocks 100 --num_tsteps 1 "
+                            "--stages_per_ts 2 --code 1"),
     "uni27_4": (4, 2, "--npx 2 --npz 2 --init_x 1 --init_y 2 --init_z 1 --nx 4 --ny 4 --nz 6 --num_vars 3 "
                       "--comm_vars 2 --stencil 27 --uniform_refine 1 --num_refine 1 --max_blocks 100 "
                       "--num_tsteps 1 --stages_per_ts 2"),

@@ -42,8 +42,8 @@ typedef struct {
    int comm_vars;       /* --comm_vars; 0 or > num_vars means num_vars
                            (main.c:711-712)                                      */
    int max_blocks;      /* --max_blocks: pool slots on this rank                 */
-   int stencil;         /* --stencil: 7 or 27 (0, the variable-work mix, is not
-                           on this path yet -> MAMR_EUNSUPPORTED)                */
+   int stencil;         /* --stencil: 7, 27, or 0 (the variable-work mix; needs
+                           mamr_set_stencil0)                                    */
    int code;            /* --code 0|1|2: all run the code-0 exchange (same result
                            on every cell the stencil reads)        */
    int permute;         /* --permute (comm.c:45-55)                              */
@@ -90,6 +90,7 @@ typedef struct {
    long long ghost_regens;                                      /* ghost layers an eliding stage
                                                                    left stale and that had to be
                                                                    regenerated on demand */
+   double total_fp_muls;                                        /* --stencil 0, stencil.c:162 ... */
 } mamr_counters;
 
 enum { MAMR_OK = 0, MAMR_ECUDA = 1, MAMR_EINVAL = 2, MAMR_EUNSUPPORTED = 3,
@@ -135,6 +136,11 @@ int mamr_set_comm_lists(mamr_ctx *ctx, const mamr_comm_dir dirs[3]);
 int mamr_comm(mamr_ctx *ctx, int start, int num_comm, int stage);
 /* stencil_driver(var, calc_stage): stencil.c:43-74 -> stencil_calc :76-145 */
 int mamr_stencil_driver(mamr_ctx *ctx, int var, int calc_stage);
+/* --stencil 0 ("variable work", stencil.c:147-983): mat, a1 and a0[mat] as init()
+ * drew them (init.c:418-423; host rand() stream).  Call once after init() and
+ * before the first stencil_driver(); calc_stage % 6 then selects the update
+ * kind and stencil_check() follows every update (stencil.c:49-70). */
+int mamr_set_stencil0(mamr_ctx *ctx, int mat, double a1, const double *a0);
 /* north_star alias: stencil_calc(var) == stencil_driver(var, 0) for 7/27 */
 int mamr_stencil_calc(mamr_ctx *ctx, int var);
 /* the same for a run of variables in one launch */

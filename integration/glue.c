@@ -86,6 +86,8 @@ static void ensure_ctx(void)
    }
    stage_tile = (double *) malloc((size_t)num_vars*tile_doubles()*sizeof(double));
    memset(&seen, 0, sizeof seen);
+   /* --stencil 0: the coefficients init() drew from rand() (init.c:418-423) */
+   if (!stencil) OK(mamr_set_stencil0(G, mat, a1, a0), "set_stencil0");
 }
 
 /* jagged blocks[n].array <-> contiguous staging tile */
@@ -207,6 +209,7 @@ static void pull_counters(void)
       size_mesg_recv[d] += c.size_mesg_recv[d] - seen.size_mesg_recv[d];
    }
    total_fp_adds += c.total_fp_adds - seen.total_fp_adds;
+   total_fp_muls += c.total_fp_muls - seen.total_fp_muls;
    total_fp_divs += c.total_fp_divs - seen.total_fp_divs;
    seen = c;
 }

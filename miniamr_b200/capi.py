@@ -51,7 +51,8 @@ class Counters(C.Structure):
                 ("size_mesg_send", C.c_double * 3), ("size_mesg_recv", C.c_double * 3),
                 ("total_fp_adds", C.c_double), ("total_fp_divs", C.c_double),
                 ("total_red", C.c_longlong), ("kernel_launches", C.c_longlong),
-                ("migrate_bytes", C.c_double), ("ghost_regens", C.c_longlong)]
+                ("migrate_bytes", C.c_double), ("ghost_regens", C.c_longlong),
+                ("total_fp_muls", C.c_double)]
 
 
 EXPORTS = [
@@ -59,7 +60,7 @@ EXPORTS = [
     "mamr_get_counters", "mamr_reset_counters", "mamr_tile_doubles", "mamr_pool_bytes",
     "mamr_upload_block", "mamr_download_block", "mamr_upload_tile",
     "mamr_download_tile", "mamr_zero_block", "mamr_upload_vars", "mamr_download_vars", "mamr_set_topology", "mamr_set_comm_lists",
-    "mamr_comm", "mamr_stencil_driver", "mamr_stencil_calc", "mamr_stencil_vars",
+    "mamr_comm", "mamr_stencil_driver", "mamr_stencil_calc", "mamr_stencil_vars", "mamr_set_stencil0",
     "mamr_check_sum", "mamr_check_sum_vars", "mamr_stage", "mamr_split_block",
     "mamr_consolidate_block", "mamr_pack_block", "mamr_unpack_block", "mamr_send_block",
     "mamr_recv_block", "mamr_stage_send_block", "mamr_stage_recv_block", "mamr_flush_block_moves",
@@ -284,6 +285,12 @@ class DeviceMesh:
 
     def stencil_driver(self, var, calc_stage=0):
         self._ck(self.L.mamr_stencil_driver(self.h, int(var), int(calc_stage)))
+
+    def set_stencil0(self, mat, a1, a0):
+        a = np.ascontiguousarray(a0, np.float64)
+        self._keep_a0 = a
+        self.L.mamr_set_stencil0.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_void_p]
+        self._ck(self.L.mamr_set_stencil0(self.h, int(mat), float(a1), a.ctypes.data))
 
     def stencil_calc(self, var):
         self._ck(self.L.mamr_stencil_calc(self.h, int(var)))

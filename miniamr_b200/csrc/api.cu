@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "stencil0.cuh"
 
 using namespace mamr;
 
@@ -199,6 +200,16 @@ struct mamr_ctx {
    bool modified_since_cs = true;
 
    int pend_start = 0, pend_num = 0;
+   int pend_stage = 0;          // calc_stage of the queued stencil calls (--stencil 0 only)
+   // --stencil 0 (stencil.c:147-983): coefficients of init.c:418-423, scratch tiles for the
+   // work[] kinds, and how often stencil_check took its two branches (flop counters)
+   bool s0_set = false;
+   int s0_mat = 0;
+   double s0_a1 = 0.0;
+   std::vector<double> s0_a0;
+   double *d_s0_a0 = nullptr, *d_s0_work = nullptr;
+   int s0_work_blocks = 0;
+   unsigned long long *d_s0_chk = nullptr, *h_s0_chk = nullptr;
 
    RefineOp *d_rops = nullptr;
    int rops_cap = 4096, rops_pos = 0;
@@ -946,6 +957,56 @@ int regen_ghosts(mamr_ctx *c, int v0, int n)
    return MAMR_OK;
 }
 
+// stencil_check books its flops per cell (stencil.c:970-971, 975-976): the kernels count
+// the two branches; the counts are folded into the counters wherever the stream is
+// synchronised anyway (check_sum, mamr_sync), never by mamr_get_counters itself
+int fold_s0_checks(mamr_ctx *c)
+{
+   if (c->p.stencil != 0 || !c->d_s0_chk) return MAMR_OK;
+   CU(cudaMemcpyAsync(c->h_s0_chk, c->d_s0_chk, 2*sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                      c->stream));
+   CU(cudaMemsetAsync(c->d_s0_chk, 0, 2*sizeof(unsigned long long), c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   const double nd = (double)c->h_s0_chk[0], nm = (double)c->h_s0_chk[1];
+   c->cnt.total_fp_divs += nd;
+   c->cnt.total_fp_adds += 2.0*nd + nm;
+   c->cnt.total_fp_muls += nm;
+   return MAMR_OK;
+}
+
+// stencil_driver() with --stencil 0 (stencil.c:43-74) for variables [v0, v0+n) of one
+// pool: variable 0 and variables >= 4*mat take the 7-point average, the others the
+// update kind pend_stage % 6 followed by stencil_check
+int run_stencil0(mamr_ctx *c, int pool, int v0, int n)
+{
+   if (c->num_active <= 0) return MAMR_OK;
+   if (!c->s0_set)
+      return fail(MAMR_EINVAL, "--stencil 0: mamr_set_stencil0 (mat, a1, a0[] of init.c:418-423) was not called");
+   const int mat = c->s0_mat, kind = c->pend_stage%6;
+   if (c->s0_work_blocks < c->num_active && kind >= S0_SEVEN) {
+      CU(cudaStreamSynchronize(c->stream));
+      if (c->d_s0_work) CU(cudaFree(c->d_s0_work));
+      c->d_s0_work = nullptr;
+      CU(cudaMalloc(&c->d_s0_work, (size_t)c->p.max_blocks*c->g.tile_stride*sizeof(double)));
+      c->s0_work_blocks = c->p.max_blocks;
+   }
+   int v = v0;
+   while (v < v0 + n) {
+      const bool plain = v == 0 || v >= 4*mat;
+      int e = v + 1;
+      while (e < v0 + n && (e == 0 || e >= 4*mat) == plain) e++;
+      KTimer t(c, KC_STENCIL);
+      if (plain)
+         launch_stencil(c->pool[pool], c->g, c->d_slots, c->num_active, v, e - v, 7, c->stream);
+      else
+         launch_stencil0(c->pool[pool], c->g, c->d_slots, c->num_active, v, e, kind, mat, c->s0_a1,
+                         c->d_s0_a0, c->d_s0_work, c->d_s0_chk, c->stream);
+      c->cnt.kernel_launches++;
+      v = e;
+   }
+   return MAMR_OK;
+}
+
 int flush_pending(mamr_ctx *c)
 {
    if (c->pend_num == 0) return MAMR_OK;
@@ -1044,10 +1105,14 @@ int flush_pending(mamr_ctx *c)
       } else {
          CK(regen_ghosts(c, r.start, r.num));   // the in-place stencil reads the stored ghosts
          for (int v = r.start; v < r.start + r.num; v++) c->zf_ok[v] = 0;
-         KTimer t(c, KC_STENCIL);
-         launch_stencil(c->pool[in], c->g, c->d_slots, c->num_active, r.start, r.num,
-                        c->p.stencil, c->stream);
-         if (c->num_active > 0) c->cnt.kernel_launches++;
+         if (c->p.stencil == 0)
+            CK(run_stencil0(c, in, r.start, r.num));
+         else {
+            KTimer t(c, KC_STENCIL);
+            launch_stencil(c->pool[in], c->g, c->d_slots, c->num_active, r.start, r.num,
+                           c->p.stencil, c->stream);
+            if (c->num_active > 0) c->cnt.kernel_launches++;
+         }
       }
    }
    CU(cudaGetLastError());
@@ -1190,8 +1255,10 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
       return fail(MAMR_EINVAL, "block size must be even and > 0 (main.c:673-684)");
    if (p.num_vars <= 0) return fail(MAMR_EINVAL, "num_vars must be > 0");
    if (p.max_blocks <= 0) return fail(MAMR_EINVAL, "max_blocks must be > 0");
-   if (p.stencil != 7 && p.stencil != 27)
-      return fail(MAMR_EUNSUPPORTED, "--stencil %d: only 7 and 27 are on the device path", p.stencil);
+   if (p.stencil != 0 && p.stencil != 7 && p.stencil != 27)
+      return fail(MAMR_EINVAL, "--stencil %d: illegal value for stencil (main.c:701-704)", p.stencil);
+   if (p.stencil == 0 && p.num_vars < 8)
+      return fail(MAMR_EINVAL, "if stencil is 0, num_vars must be more than 8 (main.c:705-708)");
    // --code 1|2 ("send ghosts", "... and process on send", comm.c:403-989,1152-1461) change
    // what travels in a message and where the restriction runs, not what the exchange
    // delivers: in the reference itself every cell the stencil reads ends up bit-identical
@@ -1240,7 +1307,7 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
    }
    c->fused_geom = fused_supported(g, why);
    const char *nf = getenv("MAMR_NO_FUSED");
-   c->use_fused = !(nf && nf[0] == '1');
+   c->use_fused = !(nf && nf[0] == '1') && p.stencil != 0;   // --stencil 0: split path + stencil0.cu
    c->fused2_geom = c->fused_geom && fused2_supported(g);
    const char *nf2 = getenv("MAMR_NO_FUSED2"), *ne = getenv("MAMR_NO_ELIDE");
    c->use_fused2 = !(nf2 && nf2[0] == '1');
@@ -1267,6 +1334,12 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
    if ((c->fused2_geom && c->use_fused2 && c->use_elide) || c->slab_geom) {
       c->zf_bytes = (size_t)2*p.nx*p.ny*p.max_blocks*p.num_vars*sizeof(double);
       for (int b = 0; b < 2; b++) CUC(cudaMalloc(&c->zf[b], c->zf_bytes));
+   }
+   if (p.stencil == 0) {
+      CUC(cudaMalloc(&c->d_s0_a0, (size_t)p.num_vars*sizeof(double)));
+      CUC(cudaMalloc(&c->d_s0_chk, 2*sizeof(unsigned long long)));
+      CUC(cudaMemsetAsync(c->d_s0_chk, 0, 2*sizeof(unsigned long long), c->stream));
+      CUC(cudaMallocHost(&c->h_s0_chk, 2*sizeof(unsigned long long)));
    }
    CUC(cudaMalloc(&c->d_sums, p.num_vars*sizeof(double)));
    CUC(cudaMallocHost(&c->h_sums, p.num_vars*sizeof(double)));
@@ -1330,6 +1403,10 @@ void mamr_destroy(mamr_ctx *c)
    if (c->h_sums) cudaFreeHost(c->h_sums);
    cudaFree(c->d_rops);
    cudaFree(c->d_payload);
+   cudaFree(c->d_s0_a0);
+   cudaFree(c->d_s0_work);
+   cudaFree(c->d_s0_chk);
+   if (c->h_s0_chk) cudaFreeHost(c->h_s0_chk);
    cudaFree(c->d_mv_send);
    cudaFree(c->d_mv_recv);
    if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -1352,6 +1429,7 @@ int mamr_sync(mamr_ctx *c)
    CK(settle_all(c));
    CK(wait_xchg(c));
    CU(cudaStreamSynchronize(c->stream));
+   CK(fold_s0_checks(c));
    return MAMR_OK;
 }
 
@@ -1658,7 +1736,7 @@ int mamr_comm(mamr_ctx *c, int start, int num_comm, int stage)
    return MAMR_OK;
 }
 
-int mamr_stencil_vars(mamr_ctx *c, int var_start, int num)
+static int stencil_vars_stage(mamr_ctx *c, int var_start, int num, int calc_stage)
 {
    if (!c) return fail(MAMR_EINVAL, "null context");
    if (var_start < 0 || num < 0 || var_start + num > c->p.num_vars)
@@ -1666,29 +1744,68 @@ int mamr_stencil_vars(mamr_ctx *c, int var_start, int num)
    if (num == 0) return MAMR_OK;
    // defer: consecutive variables are merged into one launch (driver.c:85-86
    // calls the stencil once per variable)
-   if (c->pend_num > 0 && var_start == c->pend_start + c->pend_num)
+   if (c->pend_num > 0 && var_start == c->pend_start + c->pend_num &&
+       (c->p.stencil != 0 || calc_stage == c->pend_stage))
       c->pend_num += num;
    else {
       CK(flush_pending(c));
       c->pend_start = var_start;
       c->pend_num = num;
+      c->pend_stage = calc_stage;
    }
    for (int v = var_start; v < var_start + num; v++) c->cs_valid[v] = 0;
    c->modified_since_cs = true;
-   // stencil.c:100-101, 142-143
    const double cells = (double)c->num_active*c->p.nx*c->p.ny*c->p.nz;
-   c->cnt.total_fp_divs += cells*num;
-   c->cnt.total_fp_adds += (c->p.stencil == 7 ? 6.0 : 26.0)*cells*num;
+   if (c->p.stencil != 0) {
+      // stencil.c:100-101, 142-143
+      c->cnt.total_fp_divs += cells*num;
+      c->cnt.total_fp_adds += (c->p.stencil == 7 ? 6.0 : 26.0)*cells*num;
+   } else if (c->s0_set)
+      for (int v = var_start; v < var_start + num; v++) {
+         if (v == 0 || v >= 4*c->s0_mat) {
+            c->cnt.total_fp_divs += cells;
+            c->cnt.total_fp_adds += 6.0*cells;
+         } else {
+            const S0Flops f = s0_flops(calc_stage%6, v, c->s0_mat);
+            c->cnt.total_fp_adds += f.adds*cells;
+            c->cnt.total_fp_muls += f.muls*cells;
+            c->cnt.total_fp_divs += f.divs*cells;
+         }
+      }
    return MAMR_OK;
 }
 
-int mamr_stencil_driver(mamr_ctx *c, int var, int calc_stage)
+int mamr_stencil_vars(mamr_ctx *c, int var_start, int num)
 {
-   (void)calc_stage;   // only selects the kernel for --stencil 0 (stencil.c:48-70)
-   return mamr_stencil_vars(c, var, 1);
+   if (c && c->p.stencil == 0)
+      return fail(MAMR_EINVAL, "--stencil 0: the update depends on the stage, use mamr_stencil_driver / mamr_stage");
+   return stencil_vars_stage(c, var_start, num, 0);
 }
 
-int mamr_stencil_calc(mamr_ctx *c, int var) { return mamr_stencil_vars(c, var, 1); }
+// stencil_driver(var, calc_stage), stencil.c:43-74: calc_stage only matters for
+// --stencil 0, where calc_stage % 6 selects the update kind (:51-69)
+int mamr_stencil_driver(mamr_ctx *c, int var, int calc_stage)
+{
+   return stencil_vars_stage(c, var, 1, calc_stage);
+}
+
+int mamr_set_stencil0(mamr_ctx *c, int mat, double a1, const double *a0)
+{
+   if (!c || !a0) return fail(MAMR_EINVAL, "null argument");
+   if (c->p.stencil != 0) return fail(MAMR_EINVAL, "set_stencil0: the context was not created with --stencil 0");
+   if (mat != c->p.num_vars/4) return fail(MAMR_EINVAL, "set_stencil0: mat must be num_vars/4 (init.c:419)");
+   CK(flush_pending(c));
+   c->s0_mat = mat;
+   c->s0_a1 = a1;
+   c->s0_a0.assign(a0, a0 + mat);
+   CU(cudaMemcpyAsync(c->d_s0_a0, c->s0_a0.data(), (size_t)mat*sizeof(double), cudaMemcpyHostToDevice,
+                      c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   c->s0_set = true;
+   return MAMR_OK;
+}
+
+int mamr_stencil_calc(mamr_ctx *c, int var) { return stencil_vars_stage(c, var, 1, 0); }
 
 int mamr_check_sum_vars(mamr_ctx *c, int var_start, int num, double *sums)
 {
@@ -1711,6 +1828,7 @@ int mamr_check_sum_vars(mamr_ctx *c, int var_start, int num, double *sums)
    CU(cudaMemcpyAsync(c->h_sums, c->d_sums, num*sizeof(double), cudaMemcpyDeviceToHost,
                       c->stream));
    CU(cudaStreamSynchronize(c->stream));
+   CK(fold_s0_checks(c));
    for (int i = 0; i < num; i++) {
       sums[i] = c->h_sums[i];
       c->cs_cache[var_start + i] = c->h_sums[i];
@@ -1746,7 +1864,7 @@ int mamr_stage(mamr_ctx *c, int stage)
    for (int start = 0; start < c->p.num_vars; start += c->comm_vars) {   // driver.c:75-89
       const int number = std::min(c->comm_vars, c->p.num_vars - start);
       CK(mamr_comm(c, start, number, stage));
-      CK(mamr_stencil_vars(c, start, number));
+      CK(stencil_vars_stage(c, start, number, stage));
    }
    return MAMR_OK;
 }

@@ -126,6 +126,10 @@ void launch_ghost(const FaceOp *d_ops, int n_ops, double *pool, double *send_buf
 void launch_stencil(double *pool, const Geometry &g, const int *d_slots,
                     int num_active, int var_start, int num_vars, int stencil,
                     cudaStream_t s);
+// --stencil 0 updates of variables [v0, v1) (all in 1 .. 4*mat-1), stencil0.cu
+void launch_stencil0(double *pool, const Geometry &g, const int *d_slots, int num_active, int v0, int v1,
+                     int kind, int mat, double a1, const double *d_a0, double *d_work,
+                     unsigned long long *d_chk, cudaStream_t s);
 void launch_checksum(const double *pool, const Geometry &g, const int *d_slots,
                      int num_active, int var_start, int num_vars, double *d_partials,
                      double *d_sums, cudaStream_t s);

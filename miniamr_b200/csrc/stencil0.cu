@@ -1,0 +1,139 @@
+// --stencil 0 ("variable work", stencil.c:43-74,147-983) on the device: first correct
+// path.  The per-cell arithmetic lives in stencil0.cuh (shared with the host test
+// harness); this file only decides who computes which cell when.
+//
+// Everything the updates read lies inside one block's tiles (ghost layers included,
+// filled by comm() beforehand), and the reference updates variables one after the other
+// (a later variable reads the new values of an earlier one): one CTA owns one block and
+// walks the variables of the launch in order, with a block barrier between them.
+//   kind 0        cells are independent                          -> one thread per cell
+//   kinds 1-3     in place along one axis: a cell reads the NEW value at -1 and the old
+//                 one at +1 on that axis, nothing else of its own variable
+//                                                                -> one thread per line,
+//                                                                   marching along the axis
+//   kinds 4, 5    through work[] (stencil.c:664,789)            -> all cells into a scratch
+//                                                                   tile, barrier, copy back
+//   stencil_check a second pass over the variable after its update (the sweeps read
+//                 un-checked new values, so it cannot be folded into them)
+// Tiles are read and written in global memory (L1/L2-resident: one block's tiles are a
+// few hundred KB); no shared-memory staging yet -- SURVEY.md §8f-1 is correctness first.
+// This translation unit is compiled with -fmad=false (build.py).
+#include "common.cuh"
+#include "stencil0.cuh"
+
+namespace mamr {
+
+namespace {
+
+struct S0Args {
+   double *pool;                 // variable 0 of slot 0
+   const int *slots;
+   long long var_stride, tile_stride;
+   int nx, ny, nz;
+   int v0, v1;                   // variables [v0, v1), all in 1 .. 4*mat-1
+   int kind;
+   int mat;
+   double a1;
+   const double *a0;             // device, [mat]
+   double *work;                 // [gridDim.x][tile_stride] scratch (kinds 4, 5)
+   unsigned long long *chk;      // [2]: cells stencil_check divided / scaled
+};
+
+constexpr int S0_THREADS = 256;
+
+__global__ void __launch_bounds__(S0_THREADS) stencil0_kernel(const S0Args A)
+{
+   const int tid = threadIdx.x;
+   const int nx = A.nx, ny = A.ny, nz = A.nz;
+   const long long SJ = nz + 2, PL = (long long)(ny + 2)*SJ, VS = A.var_stride;
+   double *t0 = A.pool + (long long)A.slots[blockIdx.x]*A.tile_stride;
+   double *work = A.work + (long long)blockIdx.x*A.tile_stride;
+   const S0Coef c = { A.mat, A.a1, A.a0 };
+   const int cells = nx*ny*nz;
+   unsigned long long n_div = 0, n_mul = 0;
+
+   for (int var = A.v0; var < A.v1; var++) {
+      double *tv = t0 + (long long)var*VS;
+      if (A.kind == S0_POINT) {
+         for (int e = tid; e < cells; e += S0_THREADS) {
+            const int i = e/(ny*nz) + 1, r = e%(ny*nz), j = r/nz + 1, k = r%nz + 1;
+            const long long cell = i*PL + j*SJ + k;
+            tv[cell] = s0_point(t0 + cell, VS, var, c);
+         }
+      } else if (A.kind == S0_SWEEP_I) {
+         for (int e = tid; e < ny*nz; e += S0_THREADS) {
+            const int j = e/nz + 1, k = e%nz + 1;
+            for (int i = 1; i <= nx; i++) {
+               const long long cell = i*PL + j*SJ + k;
+               tv[cell] = s0_sweep(t0 + cell, VS, var, c, PL);
+            }
+         }
+      } else if (A.kind == S0_SWEEP_J) {
+         for (int e = tid; e < nx*nz; e += S0_THREADS) {
+            const int i = e/nz + 1, k = e%nz + 1;
+            for (int j = 1; j <= ny; j++) {
+               const long long cell = i*PL + j*SJ + k;
+               tv[cell] = s0_sweep(t0 + cell, VS, var, c, SJ);
+            }
+         }
+      } else if (A.kind == S0_SWEEP_K) {
+         for (int e = tid; e < nx*ny; e += S0_THREADS) {
+            const int i = e/ny + 1, j = e%ny + 1;
+            for (int k = 1; k <= nz; k++) {
+               const long long cell = i*PL + j*SJ + k;
+               tv[cell] = s0_sweep(t0 + cell, VS, var, c, 1);
+            }
+         }
+      } else {
+         for (int e = tid; e < cells; e += S0_THREADS) {
+            const int i = e/(ny*nz) + 1, r = e%(ny*nz), j = r/nz + 1, k = r%nz + 1;
+            const long long cell = i*PL + j*SJ + k;
+            work[cell] = A.kind == S0_SEVEN ? s0_seven(t0 + cell, VS, var, c, PL, SJ)
+                                            : s0_twenty7(t0 + cell, VS, var, c, PL, SJ);
+         }
+         __syncthreads();
+         for (int e = tid; e < cells; e += S0_THREADS) {
+            const int i = e/(ny*nz) + 1, r = e%(ny*nz), j = r/nz + 1, k = r%nz + 1;
+            const long long cell = i*PL + j*SJ + k;
+            tv[cell] = work[cell];
+         }
+      }
+      __syncthreads();
+      for (int e = tid; e < cells; e += S0_THREADS) {
+         const int i = e/(ny*nz) + 1, r = e%(ny*nz), j = r/nz + 1, k = r%nz + 1;
+         const long long cell = i*PL + j*SJ + k;
+         int what;
+         tv[cell] = s0_check(tv[cell], c, &what);
+         n_div += what == 1;
+         n_mul += what == 2;
+      }
+      __syncthreads();
+   }
+   // how often stencil_check took its two branches (the reference books flops per cell)
+   for (int o = 16; o > 0; o >>= 1) {
+      n_div += __shfl_down_sync(0xffffffffu, n_div, o);
+      n_mul += __shfl_down_sync(0xffffffffu, n_mul, o);
+   }
+   if ((tid & 31) == 0) {
+      if (n_div) atomicAdd(&A.chk[0], n_div);
+      if (n_mul) atomicAdd(&A.chk[1], n_mul);
+   }
+}
+
+}  // namespace
+
+void launch_stencil0(double *pool, const Geometry &g, const int *d_slots, int num_active, int v0, int v1,
+                     int kind, int mat, double a1, const double *d_a0, double *d_work,
+                     unsigned long long *d_chk, cudaStream_t s)
+{
+   if (num_active <= 0 || v1 <= v0) return;
+   S0Args A;
+   A.pool = pool; A.slots = d_slots;
+   A.var_stride = g.var_stride; A.tile_stride = g.tile_stride;
+   A.nx = g.n[0]; A.ny = g.n[1]; A.nz = g.n[2];
+   A.v0 = v0; A.v1 = v1; A.kind = kind; A.mat = mat; A.a1 = a1; A.a0 = d_a0;
+   A.work = d_work; A.chk = d_chk;
+   stencil0_kernel<<<(unsigned)num_active, S0_THREADS, 0, s>>>(A);
+}
+
+}  // namespace mamr

@@ -287,3 +287,20 @@ void refh_exchange_dir(int dir, const double *send, double *recv)
 }
 
 void refh_barrier(void) { MPI_Barrier(MPI_COMM_WORLD); }
+
+/* --stencil 0 coefficients (init.c:418-423) and the flop counters of stencil.c */
+int refh_get_stencil0(double *a1_out, double *a0_out)
+{
+   int i;
+   if (stencil) return 0;
+   *a1_out = a1;
+   if (a0_out)
+      for (i = 0; i < mat; i++)
+         a0_out[i] = a0[i];
+   return mat;
+}
+
+void refh_get_flops(double *out)
+{
+   out[0] = total_fp_adds; out[1] = total_fp_muls; out[2] = total_fp_divs;
+}

@@ -236,5 +236,17 @@ class RefMiniAMR:
         self.lib.refh_exchange_dir(int(d), send.ctypes.data_as(C.c_void_p),
                                    recv.ctypes.data_as(C.c_void_p))
 
+    def stencil0(self):
+        """(mat, a1, a0[mat]) of a --stencil 0 run (init.c:418-423), mat = 0 otherwise"""
+        a1 = C.c_double()
+        a0 = np.zeros(max(1, self.p["num_vars"]), np.float64)
+        mat = self.lib.refh_get_stencil0(C.byref(a1), a0.ctypes.data_as(C.c_void_p))
+        return int(mat), float(a1.value), a0[:mat].copy()
+
+    def flops(self):
+        buf = (C.c_double * 3)()
+        self.lib.refh_get_flops(buf)
+        return dict(adds=buf[0], muls=buf[1], divs=buf[2])
+
     def global_active(self) -> int:
         return int(self.lib.refh_global_active())

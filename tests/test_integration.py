@@ -26,6 +26,10 @@ RUNS = {
                        f"--num_tsteps 3 --stages_per_ts 5 --refine_freq 1 {SPHERE}",
     "uni27": "--nx 4 --ny 6 --nz 4 --num_vars 3 --stencil 27 --uniform_refine 1 --num_refine 1 "
              "--init_x 2 --init_y 1 --init_z 2 --max_blocks 100 --num_tsteps 2 --stages_per_ts 5",
+    # --stencil 0: the variable-work mix; 14 stages = every update kind at least twice
+    "uni0_variable_work": "--nx 4 --ny 6 --nz 4 --num_vars 10 --comm_vars 4 --stencil 0 --uniform_refine 1 "
+                          "--num_refine 1 --init_x 2 --init_y 1 --init_z 2 --max_blocks 100 --num_tsteps 2 "
+                          "--stages_per_ts 7 --checksum_freq 3",
     "amr7_permute": f"--nx 6 --ny 4 --nz 8 --num_vars 2 --num_refine 2 --max_blocks 1000 --permute "
                     f"--refine_freq 2 --num_tsteps 4 --stages_per_ts 7 {MOVING}",
 }
@@ -67,6 +71,7 @@ def test_whole_run_matches_reference(name):
     rc, dc = ref.counters(), dev.counters()
     assert rc == dc                       # same/diff/bc face counters feed profile.c
     assert ref.timers()["fp_adds"] == dev.timers()["fp_adds"]
+    assert ref.flops() == dev.flops()
 
 
 @needs_libs

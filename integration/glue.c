@@ -59,10 +59,21 @@ static size_t tile_doubles(void)
    return (size_t)(x_block_size+2)*(y_block_size+2)*(z_block_size+2);
 }
 
+/* MAMR_VERBOSE=1: what the device layer did, printed by rank 0 when the program ends */
+static void report_at_exit(void)
+{
+   mamr_counters c;
+   if (!G || my_pe || mamr_get_counters(G, &c) != MAMR_OK) return;
+   printf("miniamr_b200: %lld kernel launches, %lld ghost-layer regenerations, %.3g bytes of migrated blocks, "
+          "%.3g bytes of ghost messages sent\n", c.kernel_launches, c.ghost_regens, c.migrate_bytes,
+          c.size_mesg_send[0] + c.size_mesg_send[1] + c.size_mesg_send[2]);
+}
+
 static void ensure_ctx(void)
 {
    mamr_params p;
    if (G) return;
+   if (getenv("MAMR_VERBOSE") && atoi(getenv("MAMR_VERBOSE"))) atexit(report_at_exit);
    memset(&p, 0, sizeof p);
    p.nx = x_block_size; p.ny = y_block_size; p.nz = z_block_size;
    p.num_vars = num_vars; p.comm_vars = comm_vars; p.max_blocks = max_num_blocks;

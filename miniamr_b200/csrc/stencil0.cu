@@ -13,8 +13,8 @@
 //                                                                   marching along the axis
 //   kinds 4, 5    through work[] (stencil.c:664,789)            -> all cells into a scratch
 //                                                                   tile, barrier, copy back
-//   stencil_check a second pass over the variable after its update (the sweeps read
-//                 un-checked new values, so it cannot be folded into them)
+//   stencil_check follows the update of a variable; folded into the update with the lag
+//                 each kind allows (the sweeps read the un-checked new value at -1)
 // Tiles are read and written in global memory (L1/L2-resident: one block's tiles are a
 // few hundred KB); no shared-memory staging yet -- SURVEY.md §8f-1 is correctness first.
 // This translation unit is compiled with -fmad=false (build.py).
@@ -39,7 +39,7 @@ struct S0Args {
    unsigned long long *chk;      // [2]: cells stencil_check divided / scaled
 };
 
-constexpr int S0_THREADS = 256;
+constexpr int S0_THREADS = 128;   // all blocks of a typical mesh resident at once (sweeps use one thread per line)
 
 __global__ void __launch_bounds__(S0_THREADS) stencil0_kernel(const S0Args A)
 {
@@ -52,37 +52,41 @@ __global__ void __launch_bounds__(S0_THREADS) stencil0_kernel(const S0Args A)
    const int cells = nx*ny*nz;
    unsigned long long n_div = 0, n_mul = 0;
 
+   // stencil_check (stencil.c:959-983) runs on the variable AFTER its update.  It is folded
+   // into the update wherever no other cell can still read the unchecked value:
+   //   kind 0      nobody reads another cell of the variable          -> checked on the spot
+   //   kinds 1-3   only the next cell of the same line reads it       -> checked one cell late
+   //   kinds 4, 5  the update lands in work[]                          -> checked while copying back
+   auto checked = [&](double x) {
+      int what;
+      x = s0_check(x, c, &what);
+      n_div += what == 1;
+      n_mul += what == 2;
+      return x;
+   };
    for (int var = A.v0; var < A.v1; var++) {
       double *tv = t0 + (long long)var*VS;
       if (A.kind == S0_POINT) {
          for (int e = tid; e < cells; e += S0_THREADS) {
             const int i = e/(ny*nz) + 1, r = e%(ny*nz), j = r/nz + 1, k = r%nz + 1;
             const long long cell = i*PL + j*SJ + k;
-            tv[cell] = s0_point(t0 + cell, VS, var, c);
+            tv[cell] = checked(s0_point(t0 + cell, VS, var, c));
          }
-      } else if (A.kind == S0_SWEEP_I) {
-         for (int e = tid; e < ny*nz; e += S0_THREADS) {
-            const int j = e/nz + 1, k = e%nz + 1;
-            for (int i = 1; i <= nx; i++) {
-               const long long cell = i*PL + j*SJ + k;
-               tv[cell] = s0_sweep(t0 + cell, VS, var, c, PL);
+      } else if (A.kind <= S0_SWEEP_K) {
+         // lines along the sweep axis; `d` = element offset of +1 on it, `len` = cells per line
+         const int len = A.kind == S0_SWEEP_I ? nx : (A.kind == S0_SWEEP_J ? ny : nz);
+         const long long d = A.kind == S0_SWEEP_I ? PL : (A.kind == S0_SWEEP_J ? SJ : 1);
+         const int lines = cells/len;
+         for (int e = tid; e < lines; e += S0_THREADS) {
+            long long cell;          // first cell of the line
+            if (A.kind == S0_SWEEP_I) cell = PL + (e/nz + 1)*SJ + (e%nz + 1);
+            else if (A.kind == S0_SWEEP_J) cell = (e/nz + 1)*PL + SJ + (e%nz + 1);
+            else cell = (e/ny + 1)*PL + (e%ny + 1)*SJ + 1;
+            for (int q = 0; q < len; q++, cell += d) {
+               tv[cell] = s0_sweep(t0 + cell, VS, var, c, d);
+               if (q > 0) tv[cell - d] = checked(tv[cell - d]);
             }
-         }
-      } else if (A.kind == S0_SWEEP_J) {
-         for (int e = tid; e < nx*nz; e += S0_THREADS) {
-            const int i = e/nz + 1, k = e%nz + 1;
-            for (int j = 1; j <= ny; j++) {
-               const long long cell = i*PL + j*SJ + k;
-               tv[cell] = s0_sweep(t0 + cell, VS, var, c, SJ);
-            }
-         }
-      } else if (A.kind == S0_SWEEP_K) {
-         for (int e = tid; e < nx*ny; e += S0_THREADS) {
-            const int i = e/ny + 1, j = e%ny + 1;
-            for (int k = 1; k <= nz; k++) {
-               const long long cell = i*PL + j*SJ + k;
-               tv[cell] = s0_sweep(t0 + cell, VS, var, c, 1);
-            }
+            tv[cell - d] = checked(tv[cell - d]);
          }
       } else {
          for (int e = tid; e < cells; e += S0_THREADS) {
@@ -95,17 +99,8 @@ __global__ void __launch_bounds__(S0_THREADS) stencil0_kernel(const S0Args A)
          for (int e = tid; e < cells; e += S0_THREADS) {
             const int i = e/(ny*nz) + 1, r = e%(ny*nz), j = r/nz + 1, k = r%nz + 1;
             const long long cell = i*PL + j*SJ + k;
-            tv[cell] = work[cell];
+            tv[cell] = checked(work[cell]);
          }
-      }
-      __syncthreads();
-      for (int e = tid; e < cells; e += S0_THREADS) {
-         const int i = e/(ny*nz) + 1, r = e%(ny*nz), j = r/nz + 1, k = r%nz + 1;
-         const long long cell = i*PL + j*SJ + k;
-         int what;
-         tv[cell] = s0_check(tv[cell], c, &what);
-         n_div += what == 1;
-         n_mul += what == 2;
       }
       __syncthreads();
    }

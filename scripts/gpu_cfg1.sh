@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+CFG1="--nx 10 --ny 10 --nz 10 --num_vars 40 --stencil 7 --num_refine 4 --max_blocks 4000 --num_objects 1 --object 2 0 0.3 0.3 0.3 0.01 0.01 0.01 0.25 0.25 0.25 0 0 0 --num_tsteps 20 --stages_per_ts 20"
+MAMR_VERBOSE=1 integration/_bin/miniAMR_b200.x $CFG1 2>&1 | grep -i "summary\|miniamr_b200\|error" | tee gpurun_out/cfg1_dropin_verbose.log
+MAMR_VERBOSE=1 MAMR_SYNC_TIMERS=1 integration/_bin/miniAMR_b200.x $CFG1 2>&1 | grep -i "summary\|miniamr_b200\|error" | tee -a gpurun_out/cfg1_dropin_verbose.log
+MAMR_VERBOSE=1 integration/_bin/miniAMR_b200.x $CFG1 --checksum_freq 20 2>&1 | grep -i "summary\|miniamr_b200\|error" | tee -a gpurun_out/cfg1_dropin_verbose.log

@@ -51,6 +51,10 @@ RUNS = {
     "uni27_code2_blocking": (2, "--npz 2 --init_x 2 --init_y 2 --init_z 1 --nx 4 --ny 4 --nz 6 --num_vars 4 "
                                 "--comm_vars 3 --stencil 27 --uniform_refine 1 --num_refine 1 --max_blocks 200 "
                                 "--num_tsteps 2 --stages_per_ts 3 --checksum_freq 1 --code 2 --blocking_send"),
+    # --stencil 0 (variable work) at 2 ranks: split-path exchange with wide faces over NCCL
+    "uni0_variable_work": (2, "--npy 2 --init_x 2 --init_y 1 --init_z 2 --nx 4 --ny 6 --nz 4 --num_vars 10 "
+                              "--comm_vars 4 --stencil 0 --uniform_refine 1 --num_refine 1 --max_blocks 100 "
+                              "--num_tsteps 2 --stages_per_ts 7 --checksum_freq 3"),
     # 4 and 8 ranks (skipped on smaller boxes): configs[3] in small at the rank grid the north star names
     "amr7_two_objects_4": (4, f"--npx 2 --npy 2 --init_x 1 --init_y 1 --init_z 2 --nx 8 --ny 8 --nz 8 --num_vars 3 "
                               f"--num_refine 3 --max_blocks 4000 --refine_freq 2 --num_tsteps 4 --stages_per_ts 4 "

@@ -121,6 +121,12 @@ int mamr_zero_block(mamr_ctx *ctx, int slot);
  * pinned memory: the buffer must stay valid until mamr_sync(). */
 int mamr_upload_vars(mamr_ctx *ctx, int var_start, int num, int num_slots, const double *host);
 int mamr_download_vars(mamr_ctx *ctx, int var_start, int num, int num_slots, double *host);
+/* The state exactly as init.c:484-495 defines it -- interiors, ghost layer zero
+ * -- for slots [0, num_slots): host[slot][var - var_start][nx][ny][nz], the
+ * block payloads of pack.c:66-70 back to back.  Fewer bytes over PCIe than
+ * whole tiles ((n/(n+2))^3), copy and scatter pipelined.  Asynchronous when
+ * `host` is pinned memory (valid until mamr_sync()). */
+int mamr_upload_interiors(mamr_ctx *ctx, int var_start, int num, int num_slots, const double *host);
 
 /* ---- topology: what comm()/stencil_calc()/check_sum() read through the
  *      globals blocks[], sorted_list, sorted_index (block.h:36-77) and the

@@ -59,7 +59,7 @@ EXPORTS = [
     "mamr_abi_version", "mamr_create", "mamr_destroy", "mamr_last_error", "mamr_sync",
     "mamr_get_counters", "mamr_reset_counters", "mamr_tile_doubles", "mamr_pool_bytes",
     "mamr_upload_block", "mamr_download_block", "mamr_upload_tile",
-    "mamr_download_tile", "mamr_zero_block", "mamr_upload_vars", "mamr_download_vars", "mamr_set_topology", "mamr_set_comm_lists",
+    "mamr_download_tile", "mamr_zero_block", "mamr_upload_vars", "mamr_download_vars", "mamr_upload_interiors", "mamr_set_topology", "mamr_set_comm_lists",
     "mamr_comm", "mamr_stencil_driver", "mamr_stencil_calc", "mamr_stencil_vars", "mamr_set_stencil0",
     "mamr_check_sum", "mamr_check_sum_vars", "mamr_stage", "mamr_split_block",
     "mamr_consolidate_block", "mamr_pack_block", "mamr_unpack_block", "mamr_send_block",
@@ -237,6 +237,12 @@ class DeviceMesh:
         """host_ptr: address of [num][num_slots][tile] doubles (pinned => asynchronous)."""
         self._ck(self.L.mamr_upload_vars(self.h, int(var_start), int(num), int(num_slots),
                                          C.c_void_p(int(host_ptr))))
+
+    def upload_interiors(self, var_start, num, num_slots, host_ptr):
+        """host_ptr: address of [num_slots][num][nx][ny][nz] doubles (interiors only, ghost layer
+        becomes zero; pinned => asynchronous)."""
+        self._ck(self.L.mamr_upload_interiors(self.h, int(var_start), int(num), int(num_slots),
+                                              C.c_void_p(int(host_ptr))))
 
     def download_vars(self, var_start, num, num_slots, host_ptr):
         self._ck(self.L.mamr_download_vars(self.h, int(var_start), int(num), int(num_slots),

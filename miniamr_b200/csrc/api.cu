@@ -155,6 +155,12 @@ struct mamr_ctx {
    // fused kernel is launched for the interior blocks on the main stream right away
    // and for the boundary blocks on `bstream`, which waits for the exchange (ev_xchg).
    // order_ord[ord] = interior blocks, then boundary blocks (each in processing order).
+   // mamr_upload_interiors: copy stream + two staging buffers (H2D of chunk k+1 runs
+   // while chunk k is scattered into the tiles)
+   cudaStream_t upstream = nullptr;
+   double *d_up[2] = {nullptr, nullptr};
+   size_t up_cap = 0;
+   cudaEvent_t ev_up_copy[2] = {nullptr, nullptr}, ev_up_fill[2] = {nullptr, nullptr};
    cudaStream_t xstream = nullptr, bstream = nullptr;
    cudaEvent_t ev_data = nullptr, ev_xchg = nullptr, ev_pre = nullptr, ev_bdone = nullptr;
    bool use_overlap = true;
@@ -194,6 +200,15 @@ struct mamr_ctx {
 
    double *d_partials = nullptr;
    size_t partials_cap = 0;
+   // partial sums the fused kernels leave behind (fused_common.cuh: cspart), CS_WARPS per
+   // tile-variable; cs_fused[v]: they describe variable v's current interiors
+   double *d_cspart = nullptr;
+   size_t cspart_cap = 0;
+   std::vector<char> cs_fused;
+   bool use_cs_fused = true;    // MAMR_NO_FUSED_CS=1
+   // ... and only while somebody asks for checksums: fused launches since the last
+   // check_sum(); beyond about three stages' worth the kernels stop producing partials
+   int launches_since_cs = 0;
    double *d_sums = nullptr, *h_sums = nullptr;
    std::vector<char> cs_valid;
    std::vector<double> cs_cache;
@@ -1049,18 +1064,25 @@ int flush_pending(mamr_ctx *c)
                v = e;
             }
          }
+         // check_sum partials ride along (every active block is covered by the launch, or by
+         // the interior + boundary pair)
+         double *cspart = (c->use_cs_fused && (slab || f2) && c->launches_since_cs < 3*c->nsets)
+                             ? c->d_cspart : nullptr;
+         c->launches_since_cs++;
+         const long long cs_stride = (long long)c->num_active*CS_WARPS;
          auto launch = [&](const int *order, int count, cudaStream_t st) {
             if (count <= 0) return;
             if (slab)
                launch_slab7(c->pool[in], c->pool[in ^ 1], c->g, c->d_slots, order,
                             count, c->d_fsrc[ord], c->d_cops[ord], c->d_cbegin[ord], recv,
-                            r.start, r.num, c->pc_start[r.start], c->zf[in], c->zf[in ^ 1], st);
+                            r.start, r.num, c->pc_start[r.start], c->zf[in], c->zf[in ^ 1], cspart,
+                            cs_stride, st);
             else if (f2)
                launch_fused2(c->pool[in], c->pool[in ^ 1], c->g, c->d_slots, order,
                              count, elide ? c->d_lops[ord] : c->d_hops[ord],
                              elide ? c->d_lbegin[ord] : c->d_hbegin[ord], recv, r.start, r.num,
                              c->pc_start[r.start], c->p.stencil, elide, c->zf[in], c->zf[in ^ 1],
-                             c->d_zsrc[ord], st);
+                             c->d_zsrc[ord], cspart, cs_stride, st);
             else
                launch_fused(c->pool[in], c->pool[in ^ 1], c->g, c->d_slots, order,
                             count, c->d_hops[ord], c->d_hbegin[ord], recv, r.start, r.num,
@@ -1098,6 +1120,7 @@ int flush_pending(mamr_ctx *c)
                c->stale_ord[v] = (signed char)ord;
                c->stale_start[v] = c->pc_start[r.start];
                c->stale_set[v] = c->pc_set[r.start];
+               c->cs_fused[v] = cspart ? 1 : 0;
                if (elide) c->shell_synced[v] = 1;
             }
          }
@@ -1233,6 +1256,7 @@ std::vector<int> processing_order(const mamr_ctx *c)
 void touch_all(mamr_ctx *c)
 {
    std::fill(c->cs_valid.begin(), c->cs_valid.end(), 0);
+   std::fill(c->cs_fused.begin(), c->cs_fused.end(), 0);
    std::fill(c->shell_synced.begin(), c->shell_synced.end(), 0);
    std::fill(c->zf_ok.begin(), c->zf_ok.end(), 0);
    c->modified_since_cs = true;
@@ -1296,6 +1320,8 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
    c->stale_start.assign(p.num_vars, 0);
    c->shell_synced.assign(p.num_vars, 0);
    c->zf_ok.assign(p.num_vars, 0);
+   c->cs_fused.assign(p.num_vars, 0);
+   { const char *e = getenv("MAMR_NO_FUSED_CS"); c->use_cs_fused = !(e && e[0] == '1'); }
    c->pc_set.assign(p.num_vars, 0);
    c->stale_set.assign(p.num_vars, 0);
    c->nsets = std::min<int>(mamr_ctx::MAX_SETS, (p.num_vars + c->comm_vars - 1)/c->comm_vars);
@@ -1399,6 +1425,7 @@ void mamr_destroy(mamr_ctx *c)
       for (int q = 0; q < mamr_ctx::MAX_SETS; q++) cudaFree(c->d_recvs[q][d]);
    }
    cudaFree(c->d_partials);
+   cudaFree(c->d_cspart);
    cudaFree(c->d_sums);
    if (c->h_sums) cudaFreeHost(c->h_sums);
    cudaFree(c->d_rops);
@@ -1413,6 +1440,12 @@ void mamr_destroy(mamr_ctx *c)
    for (int o = 0; o < 6; o++) cudaFree(c->d_order_ord[o]);
    if (c->ev_data) cudaEventDestroy(c->ev_data);
    if (c->ev_xchg) cudaEventDestroy(c->ev_xchg);
+   for (int b = 0; b < 2; b++) {
+      cudaFree(c->d_up[b]);
+      if (c->ev_up_copy[b]) cudaEventDestroy(c->ev_up_copy[b]);
+      if (c->ev_up_fill[b]) cudaEventDestroy(c->ev_up_fill[b]);
+   }
+   if (c->upstream) cudaStreamDestroy(c->upstream);
    if (c->ev_pre) cudaEventDestroy(c->ev_pre);
    if (c->ev_bdone) cudaEventDestroy(c->ev_bdone);
    if (c->xstream) cudaStreamDestroy(c->xstream);
@@ -1495,6 +1528,7 @@ int mamr_upload_tile(mamr_ctx *c, int slot, int var, const double *tile)
                       g.tile*sizeof(double), cudaMemcpyHostToDevice, c->stream));
    CU(cudaStreamSynchronize(c->stream));
    c->cs_valid[var] = 0;
+   c->cs_fused[var] = 0;
    c->shell_synced[var] = 0;
    c->zf_ok[var] = 0;
    c->modified_since_cs = true;
@@ -1539,6 +1573,59 @@ int mamr_upload_vars(mamr_ctx *c, int var_start, int num, int num_slots, const d
                            g.tile_stride*sizeof(double),
                            host + (size_t)v*num_slots*g.tile, g.tile*sizeof(double),
                            g.tile*sizeof(double), num_slots, cudaMemcpyHostToDevice, c->stream));
+   touch_all(c);
+   return MAMR_OK;
+}
+
+// The state as init.c:484-495 defines it -- interiors only, ghost layer zero -- for
+// slots [0, num_slots): host[slot][var - var_start][nx][ny][nz], i.e. the block payloads
+// of pack.c:66-70 back to back.  30 % fewer bytes over PCIe than whole tiles at 16^3;
+// the copy of one chunk overlaps the scatter of the previous one.
+int mamr_upload_interiors(mamr_ctx *c, int var_start, int num, int num_slots, const double *host)
+{
+   if (!c || !host) return fail(MAMR_EINVAL, "null argument");
+   if (var_start < 0 || num <= 0 || var_start + num > c->p.num_vars || num_slots <= 0 ||
+       num_slots > c->p.max_blocks)
+      return fail(MAMR_EINVAL, "upload_interiors: bad range vars [%d,%d) slots %d", var_start,
+                  var_start + num, num_slots);
+   CK(settle(c, var_start, num));
+   const Geometry &g = c->g;
+   const size_t per_slot = (size_t)num*c->p.nx*c->p.ny*c->p.nz;         // doubles
+   const size_t target = (size_t)16 << 20;                               // doubles per chunk (128 MB)
+   const int S = (int)std::max<size_t>(1, std::min<size_t>((size_t)num_slots, target/per_slot));
+   if (!c->upstream) {
+      CU(cudaStreamCreateWithFlags(&c->upstream, cudaStreamNonBlocking));
+      for (int b = 0; b < 2; b++) {
+         CU(cudaEventCreateWithFlags(&c->ev_up_copy[b], cudaEventDisableTiming));
+         CU(cudaEventCreateWithFlags(&c->ev_up_fill[b], cudaEventDisableTiming));
+      }
+   }
+   if ((size_t)S*per_slot > c->up_cap) {
+      CU(cudaStreamSynchronize(c->stream));
+      CU(cudaStreamSynchronize(c->upstream));
+      for (int b = 0; b < 2; b++) {
+         if (c->d_up[b]) CU(cudaFree(c->d_up[b]));
+         c->d_up[b] = nullptr;
+         CU(cudaMalloc(&c->d_up[b], (size_t)S*per_slot*sizeof(double)));
+      }
+      c->up_cap = (size_t)S*per_slot;
+   }
+   int k = 0;
+   for (int s0 = 0; s0 < num_slots; s0 += S, k++) {
+      const int b = k & 1, ns = std::min(S, num_slots - s0);
+      if (k >= 2) CU(cudaStreamWaitEvent(c->upstream, c->ev_up_fill[b], 0));   // staging b is free again
+      CU(cudaMemcpyAsync(c->d_up[b], host + (size_t)s0*per_slot, (size_t)ns*per_slot*sizeof(double),
+                         cudaMemcpyHostToDevice, c->upstream));
+      CU(cudaEventRecord(c->ev_up_copy[b], c->upstream));
+      CU(cudaStreamWaitEvent(c->stream, c->ev_up_copy[b], 0));
+      for (const Run &r : runs_of(c, var_start, num, false)) {
+         launch_fill_tiles(vpool(c, r.start), g, c->d_up[b], s0, ns, num, var_start, r.start, r.num,
+                           c->stream);
+         c->cnt.kernel_launches++;
+      }
+      CU(cudaEventRecord(c->ev_up_fill[b], c->stream));
+   }
+   CU(cudaGetLastError());
    touch_all(c);
    return MAMR_OK;
 }
@@ -1606,6 +1693,16 @@ int mamr_set_topology(mamr_ctx *c, int num_active, const mamr_block *sorted_bloc
       if (c->d_partials) CU(cudaFree(c->d_partials));
       c->partials_cap = c->slots_cap*c->p.num_vars;
       CU(cudaMalloc(&c->d_partials, c->partials_cap*sizeof(double)));
+   }
+   if (c->partials_cap != c->cspart_cap) {
+      // the fused kernels' check_sum partials: CS_WARPS slots per tile-variable, zero where
+      // a kernel has fewer compute warps
+      CU(cudaStreamSynchronize(c->stream));
+      if (c->d_cspart) CU(cudaFree(c->d_cspart));
+      c->d_cspart = nullptr;
+      c->cspart_cap = c->partials_cap;
+      CU(cudaMalloc(&c->d_cspart, c->cspart_cap*CS_WARPS*sizeof(double)));
+      CU(cudaMemsetAsync(c->d_cspart, 0, c->cspart_cap*CS_WARPS*sizeof(double), c->stream));
    }
    std::vector<int> slots(num_active);
    for (int a = 0; a < num_active; a++) slots[a] = sorted_blocks[a].slot;
@@ -1753,7 +1850,7 @@ static int stencil_vars_stage(mamr_ctx *c, int var_start, int num, int calc_stag
       c->pend_num = num;
       c->pend_stage = calc_stage;
    }
-   for (int v = var_start; v < var_start + num; v++) c->cs_valid[v] = 0;
+   for (int v = var_start; v < var_start + num; v++) c->cs_valid[v] = c->cs_fused[v] = 0;
    c->modified_since_cs = true;
    const double cells = (double)c->num_active*c->p.nx*c->p.ny*c->p.nz;
    if (c->p.stencil != 0) {
@@ -1813,11 +1910,25 @@ int mamr_check_sum_vars(mamr_ctx *c, int var_start, int num, double *sums)
    if (var_start < 0 || num <= 0 || var_start + num > c->p.num_vars)
       return fail(MAMR_EINVAL, "check_sum: bad variable range [%d,%d)", var_start, var_start + num);
    CK(flush_pending(c));
-   for (const Run &r : runs_of(c, var_start, num, false)) {
+   c->launches_since_cs = 0;
+   for (int v = var_start; v < var_start + num;) {
+      // variables whose last writer was a fused stage kernel: their partial sums are
+      // already in memory, only the fold is left
+      const bool fz = c->cs_fused[v] && c->num_active > 0;
+      int e = v + 1;
+      while (e < var_start + num && (c->cs_fused[e] && c->num_active > 0) == fz) e++;
       KTimer t(c, KC_CHECKSUM);
-      launch_checksum(vpool(c, r.start), c->g, c->d_slots, c->num_active, r.start, r.num,
-                      c->d_partials, c->d_sums + (r.start - var_start), c->stream);
-      c->cnt.kernel_launches += c->num_active > 0 ? 2 : 1;
+      if (fz) {
+         launch_checksum_final(c->d_cspart + (size_t)v*c->num_active*CS_WARPS, c->num_active*CS_WARPS,
+                               e - v, c->d_sums + (v - var_start), c->stream);
+         c->cnt.kernel_launches++;
+      } else
+         for (const Run &r : runs_of(c, v, e - v, false)) {
+            launch_checksum(vpool(c, r.start), c->g, c->d_slots, c->num_active, r.start, r.num,
+                            c->d_partials, c->d_sums + (r.start - var_start), c->stream);
+            c->cnt.kernel_launches += c->num_active > 0 ? 2 : 1;
+         }
+      v = e;
    }
    CU(cudaGetLastError());
    if (c->p.num_ranks > 1) {

@@ -126,6 +126,8 @@ void launch_ghost(const FaceOp *d_ops, int n_ops, double *pool, double *send_buf
 void launch_stencil(double *pool, const Geometry &g, const int *d_slots,
                     int num_active, int var_start, int num_vars, int stencil,
                     cudaStream_t s);
+void launch_fill_tiles(double *pool, const Geometry &g, const double *d_stage, int slot0, int nslots,
+                       int stage_vars, int var_start, int v_first, int nv, cudaStream_t s);
 // --stencil 0 updates of variables [v0, v1) (all in 1 .. 4*mat-1), stencil0.cu
 void launch_stencil0(double *pool, const Geometry &g, const int *d_slots, int num_active, int v0, int v1,
                      int kind, int mat, double a1, const double *d_a0, double *d_work,
@@ -156,7 +158,7 @@ void launch_fused2(const double *pool_in, double *pool_out, const Geometry &g, c
                    const int *d_order, int num_active, const BoxOp *d_ops, const int *d_begin,
                    const double *const recv[3], int var_start, int num_vars, int buf_var0,
                    int stencil, bool elide, const double *zf_in, double *zf_out,
-                   const long long *d_zsrc, cudaStream_t s);
+                   const long long *d_zsrc, double *d_cspart, long long cs_var_stride, cudaStream_t s);
 // Z-face exports (the k=1 and k=nz interior planes of every tile, packed)
 void launch_zface_extract(const double *pool, double *zf, const Geometry &g, const int *d_slots,
                           int num_active, int var_start, int num_vars, cudaStream_t s);
@@ -167,7 +169,11 @@ int slab7_max_cell_ops();
 void launch_slab7(const double *pool_in, double *pool_out, const Geometry &g, const int *d_slots,
                   const int *d_order, int num_active, const long long *d_fsrc, const BoxOp *d_cops,
                   const int *d_cbegin, const double *const recv[3], int var_start, int num_vars,
-                  int buf_var0, const double *zf_in, double *zf_out, cudaStream_t s);
+                  int buf_var0, const double *zf_in, double *zf_out, double *d_cspart,
+                  long long cs_var_stride, cudaStream_t s);
+constexpr int CS_WARPS = 8;   // check_sum partial slots per tile-variable the fused kernels fill (<= 8 compute warps)
+// fold `n` partials per variable (check_sum stage 2; also used on the fused kernels' partials)
+void launch_checksum_final(const double *d_partials, int n, int num_vars, double *d_sums, cudaStream_t s);
 // halo ops of every active block: pool_in (+ receive buffers) -> ghost cells of pool_out
 void launch_halo_fill(const BoxOp *d_ops, const int *d_begin, const int *d_slots, int num_active,
                       const double *pool_in, double *pool_out, const Geometry &g,

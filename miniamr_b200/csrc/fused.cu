@@ -401,6 +401,7 @@ void launch_fused(const double *pool_in, double *pool_out, const Geometry &g, co
    if (num_active <= 0 || num_vars <= 0) return;
    const FusedPlan p = make_plan(g);
    FusedArgs A;
+   A.cspart = nullptr; A.cs_var_stride = 0;
    A.pool_in = pool_in; A.pool_out = pool_out; A.slots = d_slots; A.order = d_order;
    A.ops = d_ops; A.begin = d_begin;
    for (int d = 0; d < 3; d++) A.recv[d] = recv ? recv[d] : nullptr;

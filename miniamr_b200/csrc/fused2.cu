@@ -314,6 +314,7 @@ fused2_kernel(const FusedArgs A)
    for (int t = 0; t < nv; t++) {
       const int v = v0 + t;
       double *sm = buf0 + (size_t)(t & 1)*TB;
+      double cs = 0.0;
       if (ELIDE) {
          mbar_wait(&full[t & 1], (uint32_t)((t >> 1) & 1));
          cp_async_wait_all();
@@ -375,7 +376,10 @@ fused2_kernel(const FusedArgs A)
                for (int i = 0; i < N; i++) r[q][i] = r[q][i]/7.0;
             }
 #pragma unroll
-            for (int i = 0; i < N; i++) c[(i + 1)*PL] = r[q][i];
+            for (int i = 0; i < N; i++) {
+               c[(i + 1)*PL] = r[q][i];
+               cs += r[q][i];
+            }
             if (ELIDE) {
                // columns k=1 and k=N are the Z-face exports of this tile
                const int cc = tid + q*CT, cj = cc/N, ck = cc%N;
@@ -433,6 +437,7 @@ fused2_kernel(const FusedArgs A)
                      for (int u = 0; u < 4; u++) w[u] = r[s][u]/27.0;
                   }
                   double *q0 = o + s*PL + sw, *q1 = o + s*PL + (1 - sw);
+                  cs += (w[0] + w[1]) + (w[2] + w[3]);
                   q0[0] = sw ? w[1] : w[0];
                   q1[0] = sw ? w[0] : w[1];
                   q0[SJ] = sw ? w[3] : w[2];
@@ -448,6 +453,12 @@ fused2_kernel(const FusedArgs A)
          }
       }
       prefetch_halo(t);
+      if (A.cspart) {
+         // this warp's share of check_sum(v) over the tile it has just updated
+         cs = cs_warp_sum(cs);
+         if ((tid & 31) == 0)
+            A.cspart[(long long)v*A.cs_var_stride + (long long)a*CS_WARPS + (tid >> 5)] = cs;
+      }
       // hand the updated tile to the copy warp
       fence_proxy_async();
       __syncwarp();
@@ -509,10 +520,11 @@ void launch_fused2(const double *pool_in, double *pool_out, const Geometry &g, c
                    const int *d_order, int num_active, const BoxOp *d_ops, const int *d_begin,
                    const double *const recv[3], int var_start, int num_vars, int buf_var0,
                    int stencil, bool elide, const double *zf_in, double *zf_out,
-                   const long long *d_zsrc, cudaStream_t s)
+                   const long long *d_zsrc, double *d_cspart, long long cs_var_stride, cudaStream_t s)
 {
    if (num_active <= 0 || num_vars <= 0) return;
    FusedArgs A;
+   A.cspart = d_cspart; A.cs_var_stride = cs_var_stride;
    A.pool_in = pool_in; A.pool_out = pool_out; A.slots = d_slots; A.order = d_order;
    A.ops = d_ops; A.begin = d_begin;
    for (int d = 0; d < 3; d++) A.recv[d] = recv ? recv[d] : nullptr;

@@ -28,7 +28,21 @@ struct FusedArgs {
    const long long *zsrc;
    long long zf_var_stride;
    int zf_slot;
+   // check_sum() fused into the stage (fused2.cu, slab7.cu): every compute warp adds up
+   // the interior values it has just produced and stores ONE partial per tile-variable,
+   // cspart[var*cs_var_stride + a*CS_WARPS + warp]; check_sum then only folds them
+   // (check_sum.c:36-65 without a second pass over the blocks).  nullptr = off.
+   double *cspart;
+   long long cs_var_stride;
 };
+
+
+__device__ __forceinline__ double cs_warp_sum(double v)
+{
+#pragma unroll
+   for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+   return v;
+}
 
 // compact copy of a BoxOp in shared memory
 struct SOp {

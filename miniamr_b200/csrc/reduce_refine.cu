@@ -87,6 +87,12 @@ void launch_checksum(const double *pool, const Geometry &g, const int *d_slots,
    checksum_final_kernel<<<num_vars, 256, 0, s>>>(d_partials, num_active, d_sums);
 }
 
+void launch_checksum_final(const double *d_partials, int n, int num_vars, double *d_sums, cudaStream_t s)
+{
+   if (num_vars <= 0) return;
+   checksum_final_kernel<<<num_vars, 256, 0, s>>>(d_partials, n, d_sums);
+}
+
 // ---------------------------------------------------------------------------
 // split: child o gets octant o of the parent; each parent cell / 8.0 fills the
 // 2x2x2 child cells (block.c:161-173).  grid = (ops*8, vars); one thread per
@@ -205,6 +211,32 @@ void launch_unpack_block(double *pool, const Geometry &g, int slot, int var_star
    block_payload_kernel<false><<<grid, 256, 0, s>>>(pool, slot, g.n[0], g.n[1], g.n[2],
                                                     g.tile_stride, g.var_stride,
                                                     const_cast<double *>(d_payload), var_start);
+}
+
+// mamr_upload_interiors: whole tiles (ghost layer zero, interior from the staged block
+// payloads) for slots [slot0, slot0 + nslots) x variables [v_first, v_first + nv)
+__global__ void __launch_bounds__(256)
+fill_tiles_kernel(double *pool, const double *stage, int slot0, int stage_vars, int var_start, int v_first,
+                  int nx, int ny, int nz, long long tile_stride, long long var_stride)
+{
+   const int v = v_first + blockIdx.y;
+   const int cells = nx*ny*nz, SJ = nz + 2, PL = (ny + 2)*SJ, tile = (nx + 2)*PL;
+   const double *src = stage + ((size_t)blockIdx.x*stage_vars + (v - var_start))*cells;
+   double *dst = pool + (long long)v*var_stride + (long long)(slot0 + blockIdx.x)*tile_stride;
+   for (int e = threadIdx.x; e < tile; e += blockDim.x) {
+      const int i = e/PL, r = e - i*PL, j = r/SJ, k = r - j*SJ;
+      const bool in = i >= 1 && i <= nx && j >= 1 && j <= ny && k >= 1 && k <= nz;
+      dst[e] = in ? src[((i - 1)*ny + (j - 1))*nz + (k - 1)] : 0.0;
+   }
+}
+
+void launch_fill_tiles(double *pool, const Geometry &g, const double *d_stage, int slot0, int nslots,
+                       int stage_vars, int var_start, int v_first, int nv, cudaStream_t s)
+{
+   if (nslots <= 0 || nv <= 0) return;
+   dim3 grid((unsigned)nslots, (unsigned)nv);
+   fill_tiles_kernel<<<grid, 256, 0, s>>>(pool, d_stage, slot0, stage_vars, var_start, v_first, g.n[0],
+                                           g.n[1], g.n[2], g.tile_stride, g.var_stride);
 }
 
 }  // namespace mamr

@@ -284,6 +284,7 @@ slab7_kernel(const SlabArgs B)
    }
 
    double prev[S::CPT], cur[S::CPT];
+   double cs = 0.0;                      // this thread's share of check_sum(v)
    for (int s = 0; s < total_steps; s++) {
       const int t = s/N, i = s - t*N + 1;
       const int g = t*NP + i;                               // centre plane
@@ -336,9 +337,17 @@ slab7_kernel(const SlabArgs B)
       for (int q = 0; q < S::CPT; q++) {
          if (!live[q]) continue;
          po[offO[q]] = r[q];
+         cs += r[q];
          // columns k=1 and k=N are this tile's Z-face exports
          if (offD[q] >= PL) po[N*SJ + (offD[q] - PL)] = r[q];
          if (offU[q] >= PL) po[N*SJ + (offU[q] - PL)] = r[q];
+      }
+      if (i == N && A.cspart) {
+         // last plane of variable v: one partial per warp (check_sum folds them)
+         cs = cs_warp_sum(cs);
+         if ((tid & 31) == 0)
+            A.cspart[(long long)(v0 + t)*A.cs_var_stride + (long long)a*CS_WARPS + (tid >> 5)] = cs;
+         cs = 0.0;
       }
       fence_proxy_async();
       __syncwarp();
@@ -387,11 +396,13 @@ bool slab7_configure(const Geometry &g, std::string &err)
 void launch_slab7(const double *pool_in, double *pool_out, const Geometry &g, const int *d_slots,
                   const int *d_order, int num_active, const long long *d_fsrc, const BoxOp *d_cops,
                   const int *d_cbegin, const double *const recv[3], int var_start, int num_vars,
-                  int buf_var0, const double *zf_in, double *zf_out, cudaStream_t s)
+                  int buf_var0, const double *zf_in, double *zf_out, double *d_cspart,
+                  long long cs_var_stride, cudaStream_t s)
 {
    if (num_active <= 0 || num_vars <= 0) return;
    SlabArgs B;
    FusedArgs &A = B.f;
+   A.cspart = d_cspart; A.cs_var_stride = cs_var_stride;
    A.pool_in = pool_in; A.pool_out = pool_out; A.slots = d_slots; A.order = d_order;
    A.ops = nullptr; A.begin = nullptr;
    for (int d = 0; d < 3; d++) A.recv[d] = recv ? recv[d] : nullptr;

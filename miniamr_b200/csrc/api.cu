@@ -207,7 +207,7 @@ struct mamr_ctx {
    std::vector<char> cs_fused;
    bool use_cs_fused = true;    // MAMR_NO_FUSED_CS=1
    // ... and only while somebody asks for checksums: fused launches since the last
-   // check_sum(); beyond about three stages' worth the kernels stop producing partials
+   // check_sum(); beyond about eight stages' worth the kernels stop producing partials
    int launches_since_cs = 0;
    double *d_sums = nullptr, *h_sums = nullptr;
    std::vector<char> cs_valid;
@@ -1066,7 +1066,7 @@ int flush_pending(mamr_ctx *c)
          }
          // check_sum partials ride along (every active block is covered by the launch, or by
          // the interior + boundary pair)
-         double *cspart = (c->use_cs_fused && (slab || f2) && c->launches_since_cs < 3*c->nsets)
+         double *cspart = (c->use_cs_fused && (slab || f2) && c->launches_since_cs < 8*c->nsets)
                              ? c->d_cspart : nullptr;
          c->launches_since_cs++;
          const long long cs_stride = (long long)c->num_active*CS_WARPS;

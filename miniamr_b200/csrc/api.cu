@@ -215,6 +215,18 @@ struct mamr_ctx {
    bool modified_since_cs = true;
 
    int pend_start = 0, pend_num = 0;
+   // Look-ahead over a comm group.  driver.c:85-103 interleaves stencil_driver(v) and
+   // check_sum(v) on checksum stages, which flushes one variable at a time.  The fused
+   // kernels write the OTHER pool and leave the input untouched, so the first flush also
+   // computes the variables behind it that wait under the same deferred comm(); they are
+   // committed (pool flip, flags) when the host asks for their stencil, and dropped if
+   // anything else touches them first.  spec[v]: pool[cur[v]^1] holds that result;
+   // spec_flags[v]: bit 0 eliding launch, bit 1 check_sum partials written.
+   // spec_cs[v] (valid iff spec_cs_ok[v]): check_sum of that result, folded together with an
+   // earlier variable's check_sum so that the host's next check_sum(v) is a cache hit
+   std::vector<char> spec, spec_flags, spec_cs_ok;
+   std::vector<double> spec_cs;
+   bool use_lookahead = true;   // MAMR_NO_LOOKAHEAD=1
    int pend_stage = 0;          // calc_stage of the queued stencil calls (--stencil 0 only)
    // --stencil 0 (stencil.c:147-983): coefficients of init.c:418-423, scratch tiles for the
    // work[] kinds, and how often stencil_check took its two branches (flop counters)
@@ -272,7 +284,8 @@ std::vector<Run> runs_of(const mamr_ctx *c, int v0, int n, bool split_on_comm)
       if (!r.empty()) {
          const int p = r.back().start;
          if (c->cur[p] == c->cur[v] &&
-             (!split_on_comm || (c->pc_ord[p] == c->pc_ord[v] && c->pc_start[p] == c->pc_start[v]))) {
+             (!split_on_comm || (c->pc_ord[p] == c->pc_ord[v] && c->pc_start[p] == c->pc_start[v] &&
+                                 c->spec[p] == c->spec[v]))) {
             r.back().num++;
             continue;
          }
@@ -701,7 +714,10 @@ int materialize_comm(mamr_ctx *c, int v0, int n)
       const int ord = c->pc_ord[r.start];
       if (ord < 0) continue;
       CK(comm_split(c, r.start, r.num, ord, c->pc_start[r.start], false, c->pc_set[r.start]));
-      for (int v = r.start; v < r.start + r.num; v++) c->pc_ord[v] = -1;
+      for (int v = r.start; v < r.start + r.num; v++) {
+         c->pc_ord[v] = -1;
+         c->spec[v] = 0;        // a look-ahead result for this exchange is void now
+      }
    }
    return MAMR_OK;
 }
@@ -1027,9 +1043,44 @@ int flush_pending(mamr_ctx *c)
    if (c->pend_num == 0) return MAMR_OK;
    const int v0 = c->pend_start, n = c->pend_num;
    c->pend_num = 0;
-   for (const Run &r : runs_of(c, v0, n, true)) {
+   const std::vector<Run> runs = runs_of(c, v0, n, true);
+   for (size_t ri = 0; ri < runs.size(); ri++) {
+      Run r = runs[ri];
+      const int nreq = r.num;         // variables the host has asked for
       const int ord = c->pc_ord[r.start];
       const int in = c->cur[r.start];
+      auto commit = [&](int v, bool elide, bool cs) {
+         c->cur[v] ^= 1;
+         c->stale[v] = elide ? 1 : 0;
+         c->zf_ok[v] = elide ? 1 : 0;
+         c->stale_ord[v] = (signed char)ord;
+         c->stale_start[v] = c->pc_start[v];
+         c->stale_set[v] = c->pc_set[v];
+         c->cs_fused[v] = cs ? 1 : 0;
+         if (elide) c->shell_synced[v] = 1;
+         c->spec[v] = 0;
+      };
+      if (ord >= 0 && c->spec[r.start]) {
+         // computed by an earlier launch of this comm group (look-ahead): commit only
+         for (int v = r.start; v < r.start + r.num; v++) {
+            commit(v, c->spec_flags[v] & 1, c->spec_flags[v] & 2);
+            c->pc_ord[v] = -1;
+            if (c->spec_cs_ok[v]) {      // its check_sum is known already
+               c->cs_cache[v] = c->spec_cs[v];
+               c->cs_valid[v] = 1;
+               c->spec_cs_ok[v] = 0;
+            }
+         }
+         continue;
+      }
+      if (ord >= 0 && c->use_lookahead && ri + 1 == runs.size() && c->num_active > 0) {
+         // look ahead: the variables right behind the queue that wait under the same comm()
+         int e = r.start + r.num;
+         while (e < c->p.num_vars && c->pc_ord[e] == ord && c->pc_start[e] == c->pc_start[r.start] &&
+                c->pc_set[e] == c->pc_set[r.start] && c->cur[e] == in && !c->spec[e] && !c->stale[e])
+            e++;
+         r.num = e - r.start;
+      }
       if (ord >= 0) {
          // comm() + stencil in one pass: current pool -> other pool
          double *const *rs = c->d_recvs[c->pc_set[r.start]];
@@ -1112,19 +1163,15 @@ int flush_pending(mamr_ctx *c)
             KTimer t(c, KC_STENCIL);
             launch(c->d_order, c->num_active, c->stream);
          }
-         if (c->num_active > 0) {
-            for (int v = r.start; v < r.start + r.num; v++) {
-               c->cur[v] ^= 1;
-               c->stale[v] = elide ? 1 : 0;
-               c->zf_ok[v] = elide ? 1 : 0;
-               c->stale_ord[v] = (signed char)ord;
-               c->stale_start[v] = c->pc_start[r.start];
-               c->stale_set[v] = c->pc_set[r.start];
-               c->cs_fused[v] = cspart ? 1 : 0;
-               if (elide) c->shell_synced[v] = 1;
-            }
+         if (c->num_active > 0)
+            for (int v = r.start; v < r.start + nreq; v++) commit(v, elide, cspart != nullptr);
+         for (int v = r.start; v < r.start + nreq; v++) c->pc_ord[v] = -1;
+         for (int v = r.start + nreq; v < r.start + r.num; v++) {     // looked ahead: not committed
+            if (cspart) c->cs_fused[v] = 0;   // its partials now describe the result, not the current data
+            c->spec[v] = 1;
+            c->spec_cs_ok[v] = 0;
+            c->spec_flags[v] = (char)((elide ? 1 : 0) | (cspart ? 2 : 0));
          }
-         for (int v = r.start; v < r.start + r.num; v++) c->pc_ord[v] = -1;
       } else {
          CK(regen_ghosts(c, r.start, r.num));   // the in-place stencil reads the stored ghosts
          for (int v = r.start; v < r.start + r.num; v++) c->zf_ok[v] = 0;
@@ -1257,6 +1304,7 @@ void touch_all(mamr_ctx *c)
 {
    std::fill(c->cs_valid.begin(), c->cs_valid.end(), 0);
    std::fill(c->cs_fused.begin(), c->cs_fused.end(), 0);
+   std::fill(c->spec.begin(), c->spec.end(), 0);
    std::fill(c->shell_synced.begin(), c->shell_synced.end(), 0);
    std::fill(c->zf_ok.begin(), c->zf_ok.end(), 0);
    c->modified_since_cs = true;
@@ -1321,6 +1369,11 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
    c->shell_synced.assign(p.num_vars, 0);
    c->zf_ok.assign(p.num_vars, 0);
    c->cs_fused.assign(p.num_vars, 0);
+   c->spec.assign(p.num_vars, 0);
+   c->spec_flags.assign(p.num_vars, 0);
+   c->spec_cs_ok.assign(p.num_vars, 0);
+   c->spec_cs.assign(p.num_vars, 0.0);
+   { const char *e = getenv("MAMR_NO_LOOKAHEAD"); c->use_lookahead = !(e && e[0] == '1'); }
    { const char *e = getenv("MAMR_NO_FUSED_CS"); c->use_cs_fused = !(e && e[0] == '1'); }
    c->pc_set.assign(p.num_vars, 0);
    c->stale_set.assign(p.num_vars, 0);
@@ -1930,16 +1983,34 @@ int mamr_check_sum_vars(mamr_ctx *c, int var_start, int num, double *sums)
          }
       v = e;
    }
+   // look-ahead results right behind the range: fold their partials in the same round trip
+   // (one rank only: the number of values in the all-reduce must not depend on a rank's state)
+   int extra = 0;
+   if (c->p.num_ranks == 1 && c->num_active > 0) {
+      int u = var_start + num;
+      while (u < c->p.num_vars && c->spec[u] && (c->spec_flags[u] & 2) && !c->spec_cs_ok[u]) u++;
+      extra = u - (var_start + num);
+      if (extra > 0) {
+         KTimer t(c, KC_CHECKSUM);
+         launch_checksum_final(c->d_cspart + (size_t)(var_start + num)*c->num_active*CS_WARPS,
+                               c->num_active*CS_WARPS, extra, c->d_sums + num, c->stream);
+         c->cnt.kernel_launches++;
+      }
+   }
    CU(cudaGetLastError());
    if (c->p.num_ranks > 1) {
       if (!c->nccl) return fail(MAMR_ENCCL, "check_sum: mamr_nccl_init was not called");
       NC(g_nccl.AllReduce(c->d_sums, c->d_sums, (size_t)num, NCCL_DOUBLE, NCCL_SUM, c->nccl,
                           c->stream));   // check_sum.c:57
    }
-   CU(cudaMemcpyAsync(c->h_sums, c->d_sums, num*sizeof(double), cudaMemcpyDeviceToHost,
+   CU(cudaMemcpyAsync(c->h_sums, c->d_sums, (num + extra)*sizeof(double), cudaMemcpyDeviceToHost,
                       c->stream));
    CU(cudaStreamSynchronize(c->stream));
    CK(fold_s0_checks(c));
+   for (int i = 0; i < extra; i++) {
+      c->spec_cs[var_start + num + i] = c->h_sums[num + i];
+      c->spec_cs_ok[var_start + num + i] = 1;
+   }
    for (int i = 0; i < num; i++) {
       sums[i] = c->h_sums[i];
       c->cs_cache[var_start + i] = c->h_sums[i];
@@ -1954,14 +2025,16 @@ int mamr_check_sum(mamr_ctx *c, int var, double *sum)
    if (!c || !sum) return fail(MAMR_EINVAL, "null argument");
    if (var < 0 || var >= c->p.num_vars) return fail(MAMR_EINVAL, "check_sum: bad var %d", var);
    c->cnt.total_red++;   // check_sum.c:62
-   if (c->cs_valid[var] && c->pend_num == 0) {
+   const bool had_pending = c->pend_num > 0;
+   CK(flush_pending(c));    // may commit a look-ahead result whose check_sum is known already
+   if (c->cs_valid[var]) {
       *sum = c->cs_cache[var];
       return MAMR_OK;
    }
    // init.c:681-682 asks for every variable back to back with no update in
    // between: after the first such call compute the rest in one launch
    int num = 1;
-   if (!c->modified_since_cs && c->pend_num == 0)
+   if (!c->modified_since_cs && !had_pending)
       while (var + num < c->p.num_vars && !c->cs_valid[var + num]) num++;
    std::vector<double> tmp(num);
    CK(mamr_check_sum_vars(c, var, num, tmp.data()));

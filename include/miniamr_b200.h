@@ -102,7 +102,7 @@ int  mamr_abi_version(void);
 int  mamr_create(const mamr_params *params, mamr_ctx **out);
 void mamr_destroy(mamr_ctx *ctx);
 const char *mamr_last_error(void);
-int  mamr_sync(mamr_ctx *ctx);                       /* drain all queued work   */
+int  mamr_sync(mamr_ctx *ctx);                       /* run and wait for all queued work */
 int  mamr_get_counters(mamr_ctx *ctx, mamr_counters *out);
 int  mamr_reset_counters(mamr_ctx *ctx);
 long long mamr_tile_doubles(mamr_ctx *ctx);          /* (nx+2)(ny+2)(nz+2)      */

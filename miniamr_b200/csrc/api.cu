@@ -1512,9 +1512,12 @@ void mamr_destroy(mamr_ctx *c)
 int mamr_sync(mamr_ctx *c)
 {
    if (!c) return fail(MAMR_EINVAL, "null context");
-   CK(settle_all(c));
+   // queued stencils run; a deferred comm() and ghost layers an eliding stage left stale stay
+   // lazy (whoever reads them makes them real) -- a sync must not cost a pass over the blocks
+   CK(flush_pending(c));
    CK(wait_xchg(c));
    CU(cudaStreamSynchronize(c->stream));
+   if (c->xstream) CU(cudaStreamSynchronize(c->xstream));
    CK(fold_s0_checks(c));
    return MAMR_OK;
 }

@@ -511,6 +511,148 @@ void orc_unpack_block(double *data, int nx, int ny, int nz, int num_vars,
    }
 }
 
+/* -------------------------------------------------------------------------
+ * stencil_driver() with --stencil 0, stencil.c:43-74: the "variable work" mix.
+ * mat = num_vars/4, a1, a0[mat]: init.c:418-423.  Variable 0 and variables
+ * >= 4*mat take the 7-point average.  For the others stage%6 picks
+ *   0 stencil_0 :147-226     1/2/3 stencil_x/y/z :228-659 (in place along one axis)
+ *   4 stencil_7 :661-784     5 stencil_27 :786-957        (through work[])
+ * and stencil_check :959-983 follows.  flops[0..2] += adds, muls, divs as the
+ * reference books them (per cell for stencil_check).
+ * Restated per cell with one accessor; evaluation order as C parses the
+ * reference's expressions.
+ * ---------------------------------------------------------------------- */
+#include <math.h>
+
+#define S0V(v, di, dj, dk) (base[((size_t)(v))*m.tile + (size_t)((i) + (di))*si + (size_t)((j) + (dj))*sj + (size_t)((k) + (dk))])
+#define S0C(v) S0V(v, 0, 0, 0)
+
+void orc_stencil0_driver(double *data, int nx, int ny, int nz, int num_vars, int num_active,
+                         const int *slots, int var, int stage, int mat, double a1, const double *a0,
+                         double *flops)
+{
+   orc_mesh m = mk(data, nx, ny, nz, num_vars, 0);
+   const size_t si = m.stride[0], sj = m.stride[1];
+   const int kind = stage%6;
+   const double cells = (double)nx*ny*nz;
+   int a, i, j, k, v, di, dj, dk;
+   double *work;
+
+   if (var == 0 || var >= 4*mat) {
+      orc_stencil_calc(data, nx, ny, nz, num_vars, num_active, slots, var, 7);
+      flops[0] += 6.0*cells*num_active;                           /* stencil.c:100-101 */
+      flops[2] += cells*num_active;
+      return;
+   }
+   work = (double *) malloc(m.tile*sizeof(double));
+   for (a = 0; a < num_active; a++) {
+      double *base = tile_of(&m, slots[a], 0);
+      const int q = var/mat, col = var%mat;                       /* band and column */
+      const int b1 = col + ((q + 1)%4)*mat, b2 = col + ((q + 2)%4)*mat, b3 = col + ((q + 3)%4)*mat;
+      for (i = 1; i <= nx; i++)
+         for (j = 1; j <= ny; j++)
+            for (k = 1; k <= nz; k++) {
+               double x = S0C(var), r;
+               if (kind == 0) {
+                  if (var == 1) {                                 /* :152-163 */
+                     for (v = mat; v < 2*mat; v++) x += S0C(v)*S0C(0);
+                     r = x;
+                  } else if (q == 0)                              /* :164-176 */
+                     r = x + x*(S0C(0) + S0C(1) - a1*x);
+                  else if (q == 1)                                /* :177-193 */
+                     r = x*(S0C(0) + x + a1*S0C(var + mat) + (1.0 - a1)*S0C(var + 2*mat))/S0C(1);
+                  else if (q == 2)                                /* :194-209 */
+                     r = x + S0C(var - mat)*(a1*S0C(0) + a0[var - 2*mat]*x + (1.0 - a1)*S0C(var + mat))/S0C(1);
+                  else                                            /* :210-225 */
+                     r = x + S0C(var - 2*mat)*(a1*S0C(0) + a0[var - 3*mat]*x +
+                                               (1.0 - a0[var - 3*mat])*S0C(var - mat) +
+                                               (1.0 - a1)*S0C(var - 2*mat))/(S0C(1)*S0C(1));
+                  S0C(var) = r;
+               } else if (kind <= 3) {
+                  di = kind == 1; dj = kind == 2; dk = kind == 3;   /* the sweep axis */
+                  if (var == 1) {                                 /* :234-248 */
+                     for (v = 2; v < mat + 2; v++) x += S0C(v)*S0C(0);
+                     r = x/(a1 + x);
+                  } else if (q == 0)                              /* :249-262 */
+                     r = x + x*(S0C(0) + S0C(1) - a1*x)/(a0[var] + S0C(1));
+                  else {
+                     /* slope variable: itself (q=1), var-mat (q=2), var-2mat (q=3) */
+                     const int sv = q == 1 ? var : (q == 2 ? var - mat : var - 2*mat);
+                     const double lo = S0V(var, -di, -dj, -dk), hi = S0V(var, di, dj, dk);
+                     const double t1 = fabs(S0C(sv) - S0V(sv, -di, -dj, -dk));
+                     const double t2 = fabs(S0C(sv) - S0V(sv, di, dj, dk));
+                     double den;
+                     if (q == 1)                                  /* :263-296 */
+                        den = a1 + a0[var - mat] + lo + x + hi + S0C(0) + S0C(1);
+                     else if (q == 2)                             /* :297-331 */
+                        den = a1 + a0[var - 2*mat] + S0C(var - mat) + S0C(var + mat) + lo + x + hi;
+                     else                                         /* :332-366 */
+                        den = a1 + a0[var - 3*mat] + S0C(var - mat) + S0C(var - 2*mat) + lo + x + hi;
+                     if (t1 > t2) r = (t1*lo + (t1 - t2)*(x + S0C(1)) + t2*hi)/den;
+                     else r = (t1*lo + (t2 - t1)*(x + S0C(1)) + t2*hi)/den;
+                  }
+                  S0C(var) = r;                                   /* in place: [i-1] is new, [i+1] old */
+               } else if (kind == 4) {                            /* :661-784 */
+                  work[i*si + j*sj + k] = (S0V(var, -1, 0, 0)*S0V(b1, -1, 0, 0) + S0V(var, 0, -1, 0)*S0V(b2, 0, -1, 0) +
+                                           S0V(var, 0, 0, -1)*S0V(b3, 0, 0, -1) + x*x +
+                                           S0V(var, 0, 0, 1)*S0V(b3, 0, 0, 1) + S0V(var, 0, 1, 0)*S0V(b2, 0, 1, 0) +
+                                           S0V(var, 1, 0, 0)*S0V(b1, 1, 0, 0))/7.0*(a1 + x);
+               } else {                                           /* :786-957 */
+                  double sum = 0.0;
+                  int first = 1;
+                  for (di = -1; di <= 1; di++)
+                     for (dj = -1; dj <= 1; dj++)
+                        for (dk = -1; dk <= 1; dk++) {
+                           const int dist = (di != 0) + (dj != 0) + (dk != 0);
+                           const int sv = dist == 0 ? var : (dist == 1 ? b1 : (dist == 2 ? b2 : b3));
+                           const double t = S0V(sv, di, dj, dk);
+                           sum = first ? t : sum + t;
+                           first = 0;
+                        }
+                  work[i*si + j*sj + k] = sum/(a1 + 27.0);
+               }
+            }
+      if (kind >= 4)
+         for (i = 1; i <= nx; i++)
+            for (j = 1; j <= ny; j++)
+               for (k = 1; k <= nz; k++)
+                  S0C(var) = work[i*si + j*sj + k];
+      for (i = 1; i <= nx; i++)                                   /* stencil_check :959-983 */
+         for (j = 1; j <= ny; j++)
+            for (k = 1; k <= nz; k++) {
+               double x = fabs(S0C(var));
+               if (x >= 1.0) {
+                  x /= (a1 + a0[0] + x);
+                  flops[2] += 1.0; flops[0] += 2.0;
+               } else if (x < 0.1) {
+                  x *= 10.0 - a1;
+                  flops[1] += 1.0; flops[0] += 1.0;
+               }
+               S0C(var) = x;
+            }
+   }
+   free(work);
+   {
+      /* flops per cell of the update itself, as booked at the end of each branch */
+      double ad, mu, dv;
+      if (kind == 0) {
+         if (var == 1) { ad = mat; mu = mat; dv = 0; }
+         else if (var < mat) { ad = 3; mu = 2; dv = 0; }
+         else if (var < 2*mat) { ad = 3; mu = 3; dv = 1; }
+         else if (var < 3*mat) { ad = 4; mu = 3; dv = 1; }
+         else { ad = 6; mu = 6; dv = 1; }
+      } else if (kind <= 3) {
+         if (var == 1) { ad = mat + 1; mu = mat; dv = 1; }
+         else if (var < mat) { ad = 4; mu = 2; dv = 1; }
+         else { ad = 12; mu = 3; dv = 1; }
+      } else if (kind == 4) { ad = 7; mu = 8; dv = 1; }
+      else { ad = 27; mu = 0; dv = 1; }
+      flops[0] += ad*cells*num_active; flops[1] += mu*cells*num_active; flops[2] += dv*cells*num_active;
+   }
+}
+#undef S0V
+#undef S0C
+
 /* one stage as driver.c:73-107 drives it on one rank (no checksum):
  * for each group of comm_vars variables: comm, then the stencil per variable */
 int orc_stage_local(double *data, int nx, int ny, int nz, int num_vars,

@@ -86,7 +86,20 @@ class OracleMesh:
             raise RuntimeError("ERROR: misconnected block")
         return counters.reshape(3, 3)  # [dir][same, diff, bc]
 
+    def set_stencil0(self, mat, a1, a0):
+        """--stencil 0 coefficients (init.c:418-423)"""
+        self.s0 = (int(mat), float(a1), np.ascontiguousarray(a0, np.float64))
+        self.flops = np.zeros(3)          # adds, muls, divs as stencil.c books them
+
     def stencil_driver(self, var, stage=0):
+        if self.stencil == 0:
+            mat, a1, a0 = self.s0
+            self.L.orc_stencil0_driver.argtypes = [C.c_void_p] + [C.c_int]*5 + [C.c_void_p] + [C.c_int]*3 + \
+                [C.c_double, C.c_void_p, C.c_void_p]
+            self.L.orc_stencil0_driver(self.data.ctypes.data, *self.dims, len(self.slots),
+                                       self.slots.ctypes.data, int(var), int(stage), mat, a1,
+                                       a0.ctypes.data, self.flops.ctypes.data)
+            return
         self.L.orc_stencil_calc(_p(self.data), *self.dims, len(self.slots),
                                 _p(self.slots), int(var), self.stencil)
 
@@ -95,6 +108,13 @@ class OracleMesh:
                                           _p(self.slots), int(var)))
 
     def stage(self, stage=0):
+        if self.stencil == 0:             # driver.c:75-89 with the stage-dependent update
+            for start in range(0, self.num_vars, self.comm_vars):
+                num = min(self.comm_vars, self.num_vars - start)
+                self.comm(start, num, stage)
+                for v in range(start, start + num):
+                    self.stencil_driver(v, stage)
+            return
         rc = self.L.orc_stage_local(_p(self.data), *self.dims, self.comm_vars,
                                     self.stencil, len(self.slots), _p(self.slots),
                                     _p(self.level), _p(self.nei_level), _p(self.nei),

@@ -38,6 +38,10 @@ CASES = {
                        "--max_blocks 20", 0, 2, 17),
     "ring27": ("--nx 32 --ny 32 --nz 32 --num_vars 1 --stencil 27 --uniform_refine 1 --num_refine 1 "
                "--max_blocks 20", 0, 2, 18),
+    # --stencil 0, the variable-work mix (stencil.c:147-983): 13 stages = every update kind twice;
+    # the fixture also holds mat, a1, a0[] as init() drew them (init.c:418-423)
+    "uni0_variable_work": ("--nx 6 --ny 4 --nz 8 --num_vars 14 --comm_vars 5 --stencil 0 --uniform_refine 1 "
+                           "--num_refine 1 --init_x 2 --init_y 1 --init_z 2 --max_blocks 80", 0, 13, 19),
 }
 
 
@@ -56,7 +60,10 @@ def digest(ref):
 
 
 def main():
+    only = set(sys.argv[1:])            # regenerate just these (default: all)
     for name, (args, moves, stages, seed) in CASES.items():
+        if only and name not in only:
+            continue
         r = RefMiniAMR(args.split())
         r.init()
         r.refine(0)
@@ -81,7 +88,11 @@ def main():
             for v in range(p["num_vars"]):
                 sums[st, v] = r.check_sum(v)
         out = os.path.join(HERE, name + ".npz")
-        np.savez_compressed(out, args=np.array(args), seed=seed, stages=stages,
+        extra = {}
+        if p["stencil"] == 0:
+            mat, a1, a0 = r.stencil0()
+            extra = dict(s0_mat=mat, s0_a1=a1, s0_a0=a0)
+        np.savez_compressed(out, args=np.array(args), seed=seed, stages=stages, **extra,
                             params=np.array([p[k] for k in ("nx", "ny", "nz", "num_vars", "comm_vars",
                                                              "max_blocks", "stencil", "permute")], np.int32),
                             slots=slots, level=lev, nei_level=nl, nei=ne,

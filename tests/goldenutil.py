@@ -24,6 +24,14 @@ class Golden:
         self.check_sums = z["check_sums"]
         self.sha256 = str(z["sha256"])
         self.tile_shape = (self.nx + 2, self.ny + 2, self.nz + 2)
+        # --stencil 0 fixtures: the coefficients init() drew (init.c:418-423)
+        self.stencil0 = (int(z["s0_mat"]), float(z["s0_a1"]), np.asarray(z["s0_a0"], np.float64)) \
+            if "s0_mat" in z.files else None
+
+    def apply_stencil0(self, mesh):
+        """hand the --stencil 0 coefficients to a DeviceMesh / OracleMesh (no-op for 7/27)"""
+        if self.stencil0:
+            mesh.set_stencil0(*self.stencil0)
 
     def seeded_blocks(self):
         """Yield (slot, tiles[num_vars, nx+2, ny+2, nz+2]) exactly as make_golden seeded them."""

@@ -22,6 +22,7 @@ def device_from_golden(g):
     d = DeviceMesh(g.nx, g.ny, g.nz, g.num_vars, g.max_blocks, stencil=g.stencil,
                    comm_vars=g.comm_vars, permute=g.permute)
     d.set_topology(g.slots, g.level, g.nei_level, g.nei)
+    g.apply_stencil0(d)
     for s, tiles in g.seeded_blocks():
         d.upload_block(s, tiles)
     return d

@@ -14,6 +14,7 @@ def test_oracle_reproduces_golden(name):
     m = OracleMesh(g.nx, g.ny, g.nz, g.num_vars, g.max_blocks, stencil=g.stencil,
                    comm_vars=g.comm_vars, permute=g.permute)
     m.set_topology(g.slots, g.level, g.nei_level, g.nei)
+    g.apply_stencil0(m)
     for s, tiles in g.seeded_blocks():
         m.data[s] = tiles
     for st in range(g.stages):
@@ -25,4 +26,4 @@ def test_oracle_reproduces_golden(name):
 
 def test_golden_set_is_complete():
     assert {"amr7_aniso", "amr7_moved_permute", "uni27_aniso", "uni27_permute", "cfg1_like",
-            "cfg2_like", "cfg3_like_ring", "ring27"} <= set(NAMES)
+            "cfg2_like", "cfg3_like_ring", "ring27", "uni0_variable_work"} <= set(NAMES)

@@ -23,6 +23,7 @@ def oracle_from_golden(g):
     m = OracleMesh(g.nx, g.ny, g.nz, g.num_vars, g.max_blocks, stencil=g.stencil,
                    comm_vars=g.comm_vars, permute=g.permute)
     m.set_topology(g.slots, g.level, g.nei_level, g.nei)
+    g.apply_stencil0(m)
     for s, tiles in g.seeded_blocks():
         m.data[s] = tiles
     return m

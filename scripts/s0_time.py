@@ -32,11 +32,16 @@ d.sync()
 names = ["pointwise", "sweep i", "sweep j", "sweep k", "7-pt weighted", "27-pt banded"]
 out = {}
 for kind in range(6):
+    d.sync()
+    d.kernel_timing(True)
     d.timer_begin()
     for rep in range(3):
         d.stage(6*(rep + 1) + kind)
     ms = d.timer_end()/3
-    out[names[kind]] = dict(ms_per_stage=ms, upd_per_s=nb*n**3*V/(ms*1e-3))
+    kt = d.kernel_times()
+    d.kernel_timing(False)
+    out[names[kind]] = dict(ms_per_stage=ms, upd_per_s=nb*n**3*V/(ms*1e-3),
+                            update_kernels_ms=kt["stencil_ms"]/3, ghost_exchange_ms=kt["ghost_ms"]/3)
 d.close()
 res = dict(blocks=nb, cells=n**3, num_vars=V, device=out)
 try:

@@ -288,6 +288,23 @@ def run_ours(args):
         ms = float(t.item())
     value = upd_per_step*args.steps/(ms*1e-3)
 
+    # the same loop with check_sum of every variable after every stage (--checksum_freq 1;
+    # SURVEY.md §8d "also with checksum time included"): device-resident, sums read back
+    for st in range(2):
+        d.stage(args.warmup + args.steps + st)
+        d.check_sum_vars(0, V)
+    barrier()
+    d.timer_begin()
+    for st in range(args.steps):
+        d.stage(args.warmup + args.steps + 2 + st)
+        d.check_sum_vars(0, V)
+    ms_cs = d.timer_end()
+    barrier()
+    if world > 1:
+        t = torch.tensor([ms_cs], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_cs = float(t.item())
+
     # conservation (driver.c:96-101): the average with reflective boundaries keeps
     # the per-variable sum
     sums1 = d.check_sum_vars(0, V)
@@ -390,6 +407,10 @@ def run_ours(args):
                     "reupload_every_step": {"value": strict_val, "steps": strict_steps,
                                             "h2d_bytes_per_step": h2d_bytes,
                                             "ms_per_step": strict_ms/strict_steps}},
+            "with_checksum_every_stage": {"value": upd_per_step*args.steps/(ms_cs*1e-3), "unit": UNIT,
+                                          "ms_per_step": ms_cs/args.steps,
+                                          "what": "stage + check_sum of all variables (partials produced by "
+                                                  "the stage kernel, folded and read back), device-resident"},
             "gpu_launches": int(cnt["kernel_launches"]),
             "nvlink_bytes_per_step": (sum(cnt["size_mesg_send"])/args.steps if world > 1 else 0),
             "checksum_drift": drift,

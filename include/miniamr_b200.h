@@ -45,7 +45,9 @@ typedef struct {
    int stencil;         /* --stencil: 7, 27, or 0 (the variable-work mix; needs
                            mamr_set_stencil0)                                    */
    int code;            /* --code 0|1|2: all run the code-0 exchange (same result
-                           on every cell the stencil reads)        */
+                           on every cell the stencil reads); 1|2
+                           with --permute and --stencil 27|0 differ in the
+                           reference itself -> MAMR_EUNSUPPORTED                 */
    int permute;         /* --permute (comm.c:45-55)                              */
    int device;          /* CUDA device ordinal, -1 = current device              */
    int rank, num_ranks; /* my_pe, num_pes: one process per GPU                   */

@@ -1332,13 +1332,19 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
    if (p.stencil == 0 && p.num_vars < 8)
       return fail(MAMR_EINVAL, "if stencil is 0, num_vars must be more than 8 (main.c:705-708)");
    // --code 1|2 ("send ghosts", "... and process on send", comm.c:403-989,1152-1461) change
-   // what travels in a message and where the restriction runs, not what the exchange
-   // delivers: in the reference itself every cell the stencil reads ends up bit-identical
-   // to --code 0 (tests/test_plan_multi_rank.py).  The device path therefore runs its
-   // code-0 exchange for all three; the host's comm lists keep their (larger) code-1/2
-   // offsets and each face uses the front of its slot.
+   // what travels in a message and where the restriction runs.  In the reference itself
+   // every cell the stencil reads ends up bit-identical to --code 0 -- EXCEPT with
+   // --permute and a wide stencil (27 or 0), where the ghost edges and corners a later
+   // phase forwards depend on the mode (checked at 1 and 4 ranks,
+   // tests/test_plan_multi_rank.py).  The device path runs its code-0 exchange for the
+   // equivalent combinations (the host's comm lists keep their larger code-1/2 offsets and
+   // each face uses the front of its slot) and refuses the one that is not.
    if (p.code < 0 || p.code > 2)
       return fail(MAMR_EINVAL, "--code %d: must be 0, 1 or 2 (main.c:157)", p.code);
+   if (p.code != 0 && p.permute && p.stencil != 7)
+      return fail(MAMR_EUNSUPPORTED, "--code %d with --permute and --stencil %d: the reference's ghost edges "
+                  "differ from --code 0 in this combination; only --code 0 is on the device path for it",
+                  p.code, p.stencil);
    if (p.num_ranks < 1 || p.rank < 0 || p.rank >= p.num_ranks)
       return fail(MAMR_EINVAL, "bad rank %d of %d", p.rank, p.num_ranks);
    int ndev = 0;

@@ -43,7 +43,9 @@ def test_create_rejects_bad_parameters_without_device(lib):
     from miniamr_b200 import capi
     h = C.c_void_p()
     bad = [dict(nx=3), dict(ny=0), dict(num_vars=0), dict(max_blocks=0), dict(stencil=0),
-           dict(stencil=13), dict(code=3), dict(rank=2, num_ranks=2)]
+           dict(stencil=13), dict(code=3), dict(rank=2, num_ranks=2),
+           # the one message-mode combination whose results differ from --code 0 in the reference
+           dict(code=1, permute=1, stencil=27), dict(code=2, permute=1, stencil=0, num_vars=8)]
     for kw in bad:
         base = dict(nx=4, ny=4, nz=4, num_vars=2, comm_vars=0, max_blocks=8, stencil=7, code=0,
                     permute=0, device=-1, rank=0, num_ranks=1)

@@ -10,11 +10,11 @@ import os, random, subprocess, sys, tempfile, glob, time
 ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 MPIRUN=ROOT+'/minimpi/_bin/minimpirun'
 random.seed(int(sys.argv[1]) if len(sys.argv)>1 else 1)
-grids={2:[(2,1,1),(1,2,1),(1,1,2)],3:[(3,1,1),(1,1,3)],4:[(2,2,1),(1,2,2),(4,1,1)],6:[(3,2,1),(1,2,3)],8:[(2,2,2),(4,2,1)]}
+grids={1:[(1,1,1)],2:[(2,1,1),(1,2,1),(1,1,2)],3:[(3,1,1),(1,1,3)],4:[(2,2,1),(1,2,2),(4,1,1)],6:[(3,2,1),(1,2,3)],8:[(2,2,2),(4,2,1)]}
 fails=0; n_ok=0
 t_end=time.time()+float(sys.argv[2]) if len(sys.argv)>2 else time.time()+600
 while time.time()<t_end:
-    n=random.choice([2,2,3,4,4,6,8])
+    n=int(os.environ.get("FUZZ_RANKS", 0)) or random.choice([1,2,2,3,4,4,6,8])
     npx,npy,npz=random.choice(grids[n])
     nx,ny,nz=[random.choice([2,4,6]) for _ in range(3)]
     V=random.choice([1,2,3,5]); cv=random.choice([0,1,2,V])

@@ -42,7 +42,21 @@ WORKLOADS = {
                   desc="10^3-cell blocks, 40 vars, 7-pt (configs[0] shape, uniform mesh)"),
     "cfg5": dict(n=10, num_vars=160, stencil=27, bpd=12, comm_vars=40,
                  desc="BASELINE configs[4] shape: 10^3-cell blocks, 160 vars in 4 comm groups of 40, 27-pt"),
+    # the refined mesh of BASELINE configs[0] at t=0 (sphere surface, 4 levels): topology as the
+    # unmodified reference built it (tests/golden/cfg1_v40.npz, made by tests/golden/make_golden.py);
+    # level-boundary faces take the restriction / prolongation path of the halo gather.  N=1 only.
+    "cfg1": dict(n=10, num_vars=40, stencil=7, topology="cfg1_v40",
+                 desc="BASELINE configs[0]: 10^3-cell blocks, 40 vars, 7-pt, --num_refine 4, one sphere "
+                      "(refined mesh at t=0, 785 blocks on levels 2-4)"),
 }
+
+
+def load_topology(name):
+    """block topology of a committed fixture (integers only; written by the reference)"""
+    import numpy as np
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    return dict(slots=z["slots"], level=z["level"], nei_level=z["nei_level"], nei=z["nei"],
+                max_blocks=int(z["params"][5]))
 
 
 def halo_cells(n, stencil):
@@ -56,13 +70,14 @@ def bytes_per_update(n, stencil):
     return dict(stage=16 + 24*h, stencil=16 + 8*h, ghost=16*h)
 
 
-def kernel_name(n, stencil):
+def kernel_name(n, stencil, refined=False):
     """the kernel api.cu:flush_pending launches for this block size on a uniform mesh"""
     if stencil == 7 and n == 32:
         return "slab7_kernel<32> (streamed halo gather + 7-pt stencil through a TMA plane ring; slab7.cu)"
     if n in (8, 10, 12, 16):
         return (f"fused2_kernel<{stencil},{n},elide> (halo gather + stencil, ghost stores elided, "
-                "Z faces from the export pool; fused2.cu)")
+                "Z faces from the export pool" + ("; restriction/prolongation at level boundaries" if refined else "")
+                + "; fused2.cu)")
     return f"fused_kernel<{stencil}> (halo gather + stencil; fused.cu)"
 
 
@@ -132,7 +147,7 @@ class ClockSampler:
 # reference CPU arm: the UNMODIFIED reference (oracle/_ref, openmp/ build) driven
 # stage by stage on the host cores
 # ---------------------------------------------------------------------------
-def cpu_reference(workload, steps, warmup, budget_s=None):
+def cpu_reference(workload, steps, warmup, budget_s=None, blocks=0):
     """Time `steps` stages (or as many as fit in budget_s) of the reference's own
     comm()+stencil_driver() loop on a bounded sample of the workload."""
     w = WORKLOADS[workload]
@@ -147,13 +162,30 @@ def cpu_reference(workload, steps, warmup, budget_s=None):
     if not refharness.available(variant):
         return None
     n, V = w["n"], w["num_vars"]
-    R = 3 if n <= 16 else 2                   # 512 or 64 blocks: seconds per stage at most
-    nblocks = 8**R
-    args = (f"--nx {n} --ny {n} --nz {n} --num_vars {V} --comm_vars {w.get('comm_vars', 0)} --stencil {w['stencil']} "
-            f"--uniform_refine 1 --num_refine {R} --max_blocks {nblocks + 16}").split()
+    base = (f"--nx {n} --ny {n} --nz {n} --num_vars {V} --comm_vars {w.get('comm_vars', 0)} "
+            f"--stencil {w['stencil']} ")
+    if "topology" in w:
+        # BASELINE configs[0]: the reference builds the refined mesh itself
+        args = (base + "--num_refine 4 --max_blocks 4000 --num_objects 1 "
+                "--object 2 0 0.3 0.3 0.3 0.01 0.01 0.01 0.25 0.25 0.25 0 0 0").split()
+        nblocks = None
+        shape = "refined mesh of configs[0] at t=0"
+    else:
+        # the SAME mesh as our arm's per-GPU share: bpd^3 blocks = (init * 2^R)^3
+        bpd = blocks or w["bpd"]
+        R = 0
+        while R < 4 and bpd % (2 << R) == 0:
+            R += 1
+        init = bpd >> R
+        nblocks = bpd**3
+        args = (base + f"--uniform_refine 1 --num_refine {R} --init_x {init} --init_y {init} --init_z {init} "
+                f"--max_blocks {nblocks + 16}").split()
+        shape = "uniform"
     r = refharness.RefMiniAMR(args, variant=variant)
     r.init()
     r.refine(0)
+    if nblocks is None:
+        nblocks = r.p["num_active"]
     assert r.p["num_active"] == nblocks, r.p
     upd = float(nblocks)*n**3*V
     for st in range(warmup):
@@ -174,7 +206,7 @@ def cpu_reference(workload, steps, warmup, budget_s=None):
     total = sum(times)
     return dict(value=upd*len(times)/total, unit=UNIT, cores=cores, kind=kind,
                 sample=(f"{len(times)} stages of {nblocks} blocks ({n}^3 cells, {V} vars, "
-                        f"{w['stencil']}-pt, uniform) = {upd*len(times):.3g} updates in {total:.2f} s; "
+                        f"{w['stencil']}-pt, {shape}) = {upd*len(times):.3g} updates in {total:.2f} s; "
                         f"unmodified reference {'openmp/' if variant == 'omp' else 'ref/'} build, "
                         f"gcc -O3, OMP_NUM_THREADS={cores}"),
                 ms_per_step=1e3*total/len(times), steps=len(times))
@@ -184,7 +216,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    res = cpu_reference(args.workload, args.steps, args.warmup)
+    res = cpu_reference(args.workload, args.steps, args.warmup, blocks=args.blocks)
     if res is None:
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built"}))
         return
@@ -225,68 +257,108 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    w = WORKLOADS[args.workload]
-    n, V, stencil = w["n"], w["num_vars"], w["stencil"]
-    B = args.blocks or w["bpd"]
-    nblocks = B**3
-    npx, npy, npz = rank_grid(world)
-    cv = w.get("comm_vars", V)
-    top = uniform_mesh(B, B, B, npx, npy, npz, rank, n, n, n, comm_vars=cv, stencil=stencil)
-    d = DeviceMesh(n, n, n, V, nblocks, stencil=stencil, comm_vars=cv, device=local, rank=rank,
-                   num_ranks=world)
-    d.set_topology(top["slots"], top["level"], top["nei_level"], top["nei"])
-    if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.frombuffer(bytearray(DeviceMesh.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        d.nccl_init(bytes(uid.cpu().numpy().tobytes()))
-        d.set_comm_lists(top["dirs"])
-
-    # synthetic state in pinned host memory, as init.c:484-495 defines it: interiors only
-    # (the ghost layer starts at zero), [slot][var][nx][ny][nz] = block payloads back to back
-    host = torch.empty((nblocks, V, n, n, n), dtype=torch.float64, pin_memory=True)
-    g = torch.Generator().manual_seed(1234 + rank)
-    for s0 in range(0, nblocks, 256):
-        host[s0:s0 + 256].uniform_(0.0, 1.0, generator=g)
-    h2d_bytes = host.numel()*8
-    d.upload_interiors(0, V, nblocks, host.data_ptr())
-    d.sync()
-    sums0 = d.check_sum_vars(0, V)
-
-    upd_per_step = float(nblocks)*world*n**3*V
-    bpu = bytes_per_update(n, stencil)
-
-    def barrier():
+    def barrier_all(d):
         d.sync()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing: `value` -------------------------------------
-    for st in range(args.warmup):
-        d.stage(st)
-    barrier()
-    d.reset_counters()
-    d.kernel_timing(True)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    barrier()
-    d.timer_begin()
-    for st in range(args.steps):
-        d.stage(args.warmup + st)
-    ms = d.timer_end()
-    barrier()
-    clk = clocks.stop() if rank == 0 else None
-    kt = d.kernel_times()
-    d.kernel_timing(False)
-    cnt = d.counters()
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    value = upd_per_step*args.steps/(ms*1e-3)
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    def resident_leg(wname, blocks, steps, host=None, sample_clocks=False):
+        """mesh of workload `wname` on this rank's GPU, state uploaded from pinned host memory,
+        `steps` device-resident stages timed with CUDA events (max over ranks)"""
+        w = WORKLOADS[wname]
+        n, V, stencil = w["n"], w["num_vars"], w["stencil"]
+        cv = w.get("comm_vars", V)
+        npx, npy, npz = rank_grid(world)
+        if "topology" in w:
+            if world != 1:
+                raise SystemExit(f"bench.py: workload {wname} is the reference's single-rank configuration")
+            top = load_topology(w["topology"])
+            nslots, nactive, max_blocks, B = int(top["slots"].max()) + 1, len(top["slots"]), top["max_blocks"], 0
+        else:
+            B = blocks or w["bpd"]
+            top = uniform_mesh(B, B, B, npx, npy, npz, rank, n, n, n, comm_vars=cv, stencil=stencil)
+            nslots = nactive = max_blocks = B**3
+        d = DeviceMesh(n, n, n, V, max_blocks, stencil=stencil, comm_vars=cv, device=local, rank=rank,
+                       num_ranks=world)
+        d.set_topology(top["slots"], top["level"], top["nei_level"], top["nei"])
+        if world > 1:
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid.copy_(torch.frombuffer(bytearray(DeviceMesh.nccl_unique_id()), dtype=torch.uint8))
+            dist.broadcast(uid, 0)
+            d.nccl_init(bytes(uid.cpu().numpy().tobytes()))
+            d.set_comm_lists(top["dirs"])
+        # synthetic state in pinned host memory, as init.c:484-495 defines it: interiors only
+        # (the ghost layer starts at zero), [slot][var][nx][ny][nz] = block payloads back to back
+        need = nslots*V*n**3
+        if host is None or host.numel() < need:
+            host = torch.empty(need, dtype=torch.float64, pin_memory=True)
+            g = torch.Generator().manual_seed(1234 + rank)
+            for s0 in range(0, need, 1 << 24):
+                host[s0:s0 + (1 << 24)].uniform_(0.0, 1.0, generator=g)
+        d.upload_interiors(0, V, nslots, host.data_ptr())
+        d.sync()
+        sums0 = d.check_sum_vars(0, V)
+        for st in range(args.warmup):
+            d.stage(st)
+        barrier_all(d)
+        d.reset_counters()
+        d.kernel_timing(True)
+        clocks = ClockSampler(local) if (sample_clocks and rank == 0) else None
+        if clocks:
+            clocks.start()
+        barrier_all(d)
+        d.timer_begin()
+        for st in range(steps):
+            d.stage(args.warmup + st)
+        ms = d.timer_end()
+        barrier_all(d)
+        clk = clocks.stop() if clocks else None
+        kt = d.kernel_times()
+        d.kernel_timing(False)
+        cnt = d.counters()
+        ms = max_over_ranks(ms)
+        upd = float(nactive)*world*n**3*V
+        bpu = bytes_per_update(n, stencil)
+        # one stage = the fused kernel over every block and variable of this rank (one launch per
+        # comm group; two -- interior blocks, then boundary blocks -- when an off-rank exchange
+        # overlaps the first): device time of those launches per stage
+        st_launch_ms = kt["stencil_ms"]/max(1, steps)
+        st_bytes = bpu["stencil"]*nactive*n**3*V          # per stage, this rank
+        achieved = st_bytes/(st_launch_ms*1e-3)/1e9
+        stage_gbs = upd/world*steps/(ms*1e-3)*bpu["stage"]/1e9
+        return dict(d=d, host=host, w=w, n=n, V=V, cv=cv, stencil=stencil, B=B, nslots=nslots,
+                    nactive=nactive, grid=[npx, npy, npz], sums0=sums0, ms=ms, kt=kt, cnt=cnt, clk=clk,
+                    upd_per_step=upd, value=upd*steps/(ms*1e-3), bpu=bpu, st_launch_ms=st_launch_ms,
+                    st_bytes=st_bytes, achieved=achieved, stage_gbs=stage_gbs, h2d_bytes=need*8)
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else \
+        "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+    L = resident_leg(args.workload, args.blocks, args.steps, sample_clocks=True)
+    d, host, w = L["d"], L["host"], L["w"]
+    n, V, stencil, cv, B, nblocks = L["n"], L["V"], L["stencil"], L["cv"], L["B"], L["nactive"]
+    nslots = L["nslots"]
+    npx, npy, npz = L["grid"]
+    h2d_bytes, sums0, ms, kt, cnt, clk = L["h2d_bytes"], L["sums0"], L["ms"], L["kt"], L["cnt"], L["clk"]
+    upd_per_step, value, bpu = L["upd_per_step"], L["value"], L["bpu"]
+
+    def barrier():
+        barrier_all(d)
 
     # the same loop with check_sum of every variable after every stage (--checksum_freq 1;
     # SURVEY.md §8d "also with checksum time included"): device-resident, sums read back
@@ -309,7 +381,7 @@ def run_ours(args):
     # the per-variable sum
     sums1 = d.check_sum_vars(0, V)
     drift = float(np.max(np.abs(sums1 - sums0)/np.abs(sums0)))
-    if not drift < 1e-9 and not os.environ.get("MAMR_DEBUG_SKIP"):
+    if not drift < 1e-9:
         raise SystemExit(f"bench.py: checksum drift {drift} exceeds the reference's tolerance")
 
     # ---- end to end through the reference's call surface: `e2e` ----------------
@@ -322,10 +394,10 @@ def run_ours(args):
         t0 = time.perf_counter()
         d.timer_begin()
         if not reupload_every_step:
-            d.upload_interiors(0, V, nblocks, host.data_ptr())
+            d.upload_interiors(0, V, nslots, host.data_ptr())
         for st in range(steps):
             if reupload_every_step:
-                d.upload_interiors(0, V, nblocks, host.data_ptr())
+                d.upload_interiors(0, V, nslots, host.data_ptr())
             for start in range(0, V, cv):                    # driver.c:75-89
                 d.comm(start, min(cv, V - start), st)
                 for v in range(start, min(start + cv, V)):
@@ -351,27 +423,16 @@ def run_ours(args):
 
     line = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else \
-            "fallback (B200_PROFILING.md 6.65 TB/s)"
-        # one stage = the fused kernel over every block and variable of this rank (one
-        # launch; two -- interior blocks, then boundary blocks -- when an off-rank
-        # exchange overlaps the first): device time of those launches per stage
-        st_launch_ms = kt["stencil_ms"]/max(1, args.steps)
-        st_bytes = bpu["stencil"]*nblocks*n**3*V          # per stage, this rank
-        achieved = st_bytes/(st_launch_ms*1e-3)/1e9
-        traffic = None
+        st_launch_ms, st_bytes, achieved = L["st_launch_ms"], L["st_bytes"], L["achieved"]
+        traffic = traffic_src = None
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             traffic = tr.get(f"{args.workload}:{B}", {}).get("fused_bytes_per_launch")
+            traffic_src = tr.get(f"{args.workload}:{B}", {}).get("source")
         except Exception:
             pass
-        stage_gbs = value/world*bpu["stage"]/1e9
+        stage_gbs = L["stage_gbs"]
+        active_bytes = nblocks*(n + 2)**3*V*8
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms/args.steps,
@@ -381,13 +442,15 @@ def run_ours(args):
                        "blocks_per_gpu": nblocks, "cells_per_block": n**3, "num_vars": V, "comm_vars": cv,
                        "stencil": stencil, "rank_grid": [npx, npy, npz],
                        "bytes_per_gpu": d.pool_bytes(),
-                       "cache": (f"no flush needed: every stage streams the whole pool "
-                                 f"({d.pool_bytes()/2/1e9:.1f} GB per GPU) >> 126 MB L2")},
+                       "cache": (f"no flush needed: every stage streams all active tiles "
+                                 f"({active_bytes/1e9:.2f} GB per GPU, read from one pool and written to the "
+                                 f"other) >> 126 MB L2")},
             "roofline": {"bound": "hbm",
-                         "kernel": kernel_name(n, stencil),
+                         "kernel": kernel_name(n, stencil, "topology" in w),
                          "launches_per_step": kt["stencil_launches"]/max(1, args.steps),
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved/peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved/peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": st_bytes,
                          "launch_ms": st_launch_ms,
                          "stage_bytes_per_update": bpu["stage"],
@@ -416,11 +479,37 @@ def run_ours(args):
             "checksum_drift": drift,
         }
     d.close()
+    # The other BASELINE configurations, device-resident, in the same run (the headline stays
+    # configs[1] at every N so that the per-N values are comparable): configs[2] (cfg3, the
+    # weak-scaling 32^3 7-point mesh) at every N, the refined configs[0] mesh (cfg1) at N=1.
+    also = {}
+    if args.workload == "cfg2" and not args.no_also:
+        for wn in (["cfg3"] + (["cfg1"] if world == 1 else [])):
+            try:
+                A = resident_leg(wn, 0, args.steps, host=host)
+                host = A["host"]
+                A["d"].close()
+                also[wn] = {"workload": WORKLOADS[wn]["desc"], "value": A["value"], "unit": UNIT,
+                            "ms_per_step": A["ms"]/args.steps, "blocks_per_gpu": A["nactive"],
+                            "roofline": {"kernel": kernel_name(A["n"], A["stencil"], "topology" in A["w"]),
+                                         "achieved": A["achieved"], "peak": peak, "unit": "GB/s",
+                                         "frac": A["achieved"]/peak, "launch_ms": A["st_launch_ms"],
+                                         "launches_per_step": A["kt"]["stencil_launches"]/max(1, args.steps),
+                                         "algorithmic_bytes_per_launch": A["st_bytes"],
+                                         "stage_frac": A["stage_gbs"]/peak,
+                                         "kernel_share_of_step": {"stencil": A["kt"]["stencil_ms"]/A["ms"],
+                                                                  "ghost": A["kt"]["ghost_ms"]/A["ms"]}},
+                            "nvlink_bytes_per_step": (sum(A["cnt"]["size_mesg_send"])/args.steps
+                                                      if world > 1 else 0)}
+            except Exception as e:       # never gates the headline
+                also[wn] = {"failed": str(e)}
     del host
     if rank == 0:
+        if also:
+            line["also"] = also
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cb = cpu_reference(args.workload, 0, 1, budget_s=args.cpu_seconds)
+                cb = cpu_reference(args.workload, 0, 1, budget_s=args.cpu_seconds, blocks=args.blocks)
                 if cb:
                     line["cpu_baseline"] = {k: cb[k] for k in
                                             ("value", "unit", "cores", "kind", "sample")}
@@ -443,6 +532,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=0, help="blocks per edge per GPU (default per workload)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the cfg3 / cfg1 device-resident legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -52,17 +52,27 @@ def build(force: bool = False, verbose: bool = False) -> str:
     # files whose arithmetic must follow the reference's expression trees operation by
     # operation are compiled without FMA contraction (the other kernels only add and use
     # explicit fma() where they mean it)
-    objs = []
+    # one object per source, compiled in parallel; an object is reused while it is newer than
+    # its source and every header
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hdr_t = max(os.path.getmtime(d) for d in DEPS if not d.endswith(".cu"))
+    jobs, objs = [], []
     for src in SRCS:
-        if os.path.basename(src) in NO_FMA:
-            os.makedirs(OBJ_DIR, exist_ok=True)
-            obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
-            cmd = common + ["-fmad=false", "-c", src, "-o", obj]
-            print(" ".join(cmd), flush=True)
-            subprocess.check_call(cmd, env=env)
-            objs.append(obj)
-    rest = [s for s in SRCS if os.path.basename(s) not in NO_FMA]
-    cmd = common + ["-shared", "-Xlinker", "-soname=libminiamr_b200.so", "-o", LIB] + rest + objs + ["-ldl"]
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= max(os.path.getmtime(src), hdr_t):
+            continue
+        cmd = common + (["-fmad=false"] if os.path.basename(src) in NO_FMA else []) + ["-c", src, "-o", obj]
+        jobs.append(cmd)
+
+    def run(cmd):
+        print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd, env=env)
+
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
+        list(ex.map(run, jobs))
+    cmd = common + ["-shared", "-Xlinker", "-soname=libminiamr_b200.so", "-o", LIB] + objs + ["-ldl"]
     print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd, env=env)
     return LIB

@@ -161,6 +161,7 @@ struct mamr_ctx {
    double *d_up[2] = {nullptr, nullptr};
    size_t up_cap = 0;
    cudaEvent_t ev_up_copy[2] = {nullptr, nullptr}, ev_up_fill[2] = {nullptr, nullptr};
+   bool up_fill_rec[2] = {false, false};   // ev_up_fill[b] has been recorded (by this or an earlier call)
    cudaStream_t xstream = nullptr, bstream = nullptr;
    cudaEvent_t ev_data = nullptr, ev_xchg = nullptr, ev_pre = nullptr, ev_bdone = nullptr;
    bool use_overlap = true;
@@ -210,7 +211,7 @@ struct mamr_ctx {
    // check_sum(); beyond about eight stages' worth the kernels stop producing partials
    int launches_since_cs = 0;
    double *d_sums = nullptr, *h_sums = nullptr;
-   std::vector<char> cs_valid;
+   std::vector<char> cs_valid, cs_local_dirty;
    std::vector<double> cs_cache;
    bool modified_since_cs = true;
 
@@ -1300,14 +1301,26 @@ std::vector<int> processing_order(const mamr_ctx *c)
    return order;
 }
 
-void touch_all(mamr_ctx *c)
+// Block data changed behind the stencil's back.  With more than one rank check_sum() is a
+// collective: whether a rank joins it (or serves its cache) and how many variables it reduces
+// may only depend on events every rank sees -- stencil calls, mamr_set_topology,
+// mamr_flush_block_moves (`uniform`).  A rank-local change (upload, split, consolidate,
+// unpack) therefore leaves the cache decision alone and marks the cached sums as not
+// servable: check_sum() of such a variable without a uniform event in between is an error,
+// not a hang.
+void touch_all(mamr_ctx *c, bool uniform = false)
 {
-   std::fill(c->cs_valid.begin(), c->cs_valid.end(), 0);
+   if (c->p.num_ranks > 1 && !uniform)
+      std::fill(c->cs_local_dirty.begin(), c->cs_local_dirty.end(), 1);
+   else {
+      std::fill(c->cs_valid.begin(), c->cs_valid.end(), 0);
+      std::fill(c->cs_local_dirty.begin(), c->cs_local_dirty.end(), 0);
+      c->modified_since_cs = true;
+   }
    std::fill(c->cs_fused.begin(), c->cs_fused.end(), 0);
    std::fill(c->spec.begin(), c->spec.end(), 0);
    std::fill(c->shell_synced.begin(), c->shell_synced.end(), 0);
    std::fill(c->zf_ok.begin(), c->zf_ok.end(), 0);
-   c->modified_since_cs = true;
 }
 
 }  // namespace
@@ -1365,6 +1378,7 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
    g.var_stride = g.tile_stride*p.max_blocks;
    memset(&c->cnt, 0, sizeof c->cnt);
    c->cs_valid.assign(p.num_vars, 0);
+   c->cs_local_dirty.assign(p.num_vars, 0);
    c->cs_cache.assign(p.num_vars, 0.0);
    c->cur.assign(p.num_vars, 0);
    c->pc_ord.assign(p.num_vars, -1);
@@ -1589,11 +1603,14 @@ int mamr_upload_tile(mamr_ctx *c, int slot, int var, const double *tile)
    CU(cudaMemcpyAsync(vpool(c, var) + (long long)var*g.var_stride + tile_base(g, slot), tile,
                       g.tile*sizeof(double), cudaMemcpyHostToDevice, c->stream));
    CU(cudaStreamSynchronize(c->stream));
-   c->cs_valid[var] = 0;
+   if (c->p.num_ranks > 1) c->cs_local_dirty[var] = 1;      // see touch_all
+   else {
+      c->cs_valid[var] = 0;
+      c->modified_since_cs = true;
+   }
    c->cs_fused[var] = 0;
    c->shell_synced[var] = 0;
    c->zf_ok[var] = 0;
-   c->modified_since_cs = true;
    return MAMR_OK;
 }
 
@@ -1669,13 +1686,16 @@ int mamr_upload_interiors(mamr_ctx *c, int var_start, int num, int num_slots, co
          if (c->d_up[b]) CU(cudaFree(c->d_up[b]));
          c->d_up[b] = nullptr;
          CU(cudaMalloc(&c->d_up[b], (size_t)S*per_slot*sizeof(double)));
+         c->up_fill_rec[b] = false;
       }
       c->up_cap = (size_t)S*per_slot;
    }
    int k = 0;
    for (int s0 = 0; s0 < num_slots; s0 += S, k++) {
       const int b = k & 1, ns = std::min(S, num_slots - s0);
-      if (k >= 2) CU(cudaStreamWaitEvent(c->upstream, c->ev_up_fill[b], 0));   // staging b is free again
+      // staging b is free again: the scatter that last read it (in this call or in an earlier,
+      // still queued one) has finished
+      if (c->up_fill_rec[b]) CU(cudaStreamWaitEvent(c->upstream, c->ev_up_fill[b], 0));
       CU(cudaMemcpyAsync(c->d_up[b], host + (size_t)s0*per_slot, (size_t)ns*per_slot*sizeof(double),
                          cudaMemcpyHostToDevice, c->upstream));
       CU(cudaEventRecord(c->ev_up_copy[b], c->upstream));
@@ -1686,6 +1706,7 @@ int mamr_upload_interiors(mamr_ctx *c, int var_start, int num, int num_slots, co
          c->cnt.kernel_launches++;
       }
       CU(cudaEventRecord(c->ev_up_fill[b], c->stream));
+      c->up_fill_rec[b] = true;
    }
    CU(cudaGetLastError());
    touch_all(c);
@@ -1780,7 +1801,7 @@ int mamr_set_topology(mamr_ctx *c, int num_active, const mamr_block *sorted_bloc
    CU(cudaStreamSynchronize(c->stream));
    c->ops_dirty = true;
    for (int o = 0; o < 6; o++) c->plan_built[o] = false;
-   touch_all(c);
+   touch_all(c, true);
    return MAMR_OK;
 }
 
@@ -1825,6 +1846,10 @@ int mamr_comm(mamr_ctx *c, int start, int num_comm, int stage)
    if (!c) return fail(MAMR_EINVAL, "null context");
    if (start < 0 || num_comm < 0 || start + num_comm > c->p.num_vars)
       return fail(MAMR_EINVAL, "comm: bad variable range [%d,%d)", start, start + num_comm);
+   // the message buffers hold comm_vars variables per face (comm_util.c:50-75, driver.c:75-89)
+   if (c->have_partners && num_comm > c->comm_vars)
+      return fail(MAMR_EINVAL, "comm: %d variables in one call, but the message buffers are sized for "
+                  "--comm_vars %d", num_comm, c->comm_vars);
    // a queued stencil or an earlier deferred comm() of these variables comes first
    CK(settle_data(c, start, num_comm));
    if (c->ops_dirty) CK(build_ops(c));   // also validates the topology (comm.c:198-201)
@@ -1912,7 +1937,7 @@ static int stencil_vars_stage(mamr_ctx *c, int var_start, int num, int calc_stag
       c->pend_num = num;
       c->pend_stage = calc_stage;
    }
-   for (int v = var_start; v < var_start + num; v++) c->cs_valid[v] = c->cs_fused[v] = 0;
+   for (int v = var_start; v < var_start + num; v++) c->cs_valid[v] = c->cs_fused[v] = c->cs_local_dirty[v] = 0;
    c->modified_since_cs = true;
    const double cells = (double)c->num_active*c->p.nx*c->p.ny*c->p.nz;
    if (c->p.stencil != 0) {
@@ -2024,6 +2049,7 @@ int mamr_check_sum_vars(mamr_ctx *c, int var_start, int num, double *sums)
       sums[i] = c->h_sums[i];
       c->cs_cache[var_start + i] = c->h_sums[i];
       c->cs_valid[var_start + i] = 1;
+      c->cs_local_dirty[var_start + i] = 0;
    }
    c->modified_since_cs = false;
    return MAMR_OK;
@@ -2037,6 +2063,11 @@ int mamr_check_sum(mamr_ctx *c, int var, double *sum)
    const bool had_pending = c->pend_num > 0;
    CK(flush_pending(c));    // may commit a look-ahead result whose check_sum is known already
    if (c->cs_valid[var]) {
+      if (c->cs_local_dirty[var])
+         return fail(MAMR_EINVAL, "check_sum(%d): this rank's blocks changed (upload / split / consolidate / "
+                     "unpack) since the sum was reduced and no collective event (stencil, mamr_set_topology, "
+                     "mamr_flush_block_moves) followed; the cached sum is stale and the all-reduce cannot be "
+                     "joined by one rank alone", var);
       *sum = c->cs_cache[var];
       return MAMR_OK;
    }
@@ -2258,6 +2289,13 @@ int mamr_pending_block_moves(mamr_ctx *c)
 int mamr_flush_block_moves(mamr_ctx *c)
 {
    if (!c) return fail(MAMR_EINVAL, "null context");
+   // every rank calls this at the same program point, also ranks that move nothing: a
+   // collectively uniform invalidation of the check_sum cache (see touch_all)
+   if (c->p.num_ranks > 1) {
+      std::fill(c->cs_valid.begin(), c->cs_valid.end(), 0);
+      std::fill(c->cs_local_dirty.begin(), c->cs_local_dirty.end(), 0);
+      c->modified_since_cs = true;
+   }
    if (c->mv_send.empty() && c->mv_recv.empty()) return MAMR_OK;
    if (!c->nccl) return fail(MAMR_ENCCL, "flush_block_moves: mamr_nccl_init was not called");
    CK(settle_all(c));
@@ -2277,7 +2315,7 @@ int mamr_flush_block_moves(mamr_ctx *c)
       }
    CU(cudaGetLastError());
    c->cnt.migrate_bytes += (double)c->mv_send.size()*n*sizeof(double);
-   if (!c->mv_recv.empty()) touch_all(c);
+   if (!c->mv_recv.empty()) touch_all(c, true);
    c->mv_send.clear();
    c->mv_recv.clear();
    return MAMR_OK;

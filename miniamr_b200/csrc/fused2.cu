@@ -223,13 +223,6 @@ fused2_kernel(const FusedArgs A)
          soff[q] = (int)(s.src_base + o);
          dinfo[q] = dsto | (lo << 20) | (mode << 26) | (s.src_mem << 29);
          if (mode != FM_COPY || s.src_mem != BM_POOL) plain = false;
-         // perf experiments only (MAMR_DEBUG_SKIP): drop the Z-face cells / every cell
-         if (((A.chunk & 1) && dsto >= TILE) || (A.chunk & 2)) dinfo[q] = -1;
-         if (dsto < TILE) {
-            const int dk = dsto%SJ;
-            const bool kg = dk == 0 || dk == N + 1;
-            if (((A.chunk & 4) && kg) || ((A.chunk & 8) && !kg)) dinfo[q] = -1;
-         }
       }
    }
    const int nplain = __popc(__ballot_sync(0xffffffffu, plain));
@@ -534,14 +527,12 @@ void launch_fused2(const double *pool_in, double *pool_out, const Geometry &g, c
    A.zf_in = zf_in; A.zf_out = zf_out; A.zsrc = d_zsrc;
    A.zf_slot = 2*g.n[0]*g.n[1];
    A.zf_var_stride = (long long)A.zf_slot*(g.var_stride/g.tile_stride);
-   static int vpc_env = -1, dbg_env = 0;
+   static int vpc_env = -1;
    if (vpc_env < 0) {
       const char *e = getenv("MAMR_VPC");
       vpc_env = e ? atoi(e) : 0;
-      const char *d = getenv("MAMR_DEBUG_SKIP");
-      dbg_env = d ? atoi(d) : 0;
    }
-   A.chunk = dbg_env;
+   A.chunk = 0;
    A.vpc = vpc_env > 0 ? vpc_env : 20;
    if (A.vpc > num_vars) A.vpc = num_vars;
    A.var_start = var_start;

@@ -40,6 +40,15 @@ CASES = {
                "--max_blocks 20", 0, 2, 18),
     # --stencil 0, the variable-work mix (stencil.c:147-983): 13 stages = every update kind twice;
     # the fixture also holds mat, a1, a0[] as init() drew them (init.c:418-423)
+    # BASELINE variable counts (the bench's per-CTA variable pipelines run 10-20 tiles deep, cfg5 uses
+    # four receive-buffer sets): same shapes as BASELINE.json configs[1], [2], [4], [0]
+    "cfg2_v40": ("--nx 16 --ny 16 --nz 16 --num_vars 40 --stencil 27 --uniform_refine 1 --num_refine 2 "
+                 "--max_blocks 80", 0, 2, 21),
+    "cfg3_v40": ("--nx 32 --ny 32 --nz 32 --num_vars 40 --stencil 7 --uniform_refine 1 --num_refine 1 "
+                 "--max_blocks 20", 0, 2, 22),
+    "cfg5_v160": ("--nx 10 --ny 10 --nz 10 --num_vars 160 --comm_vars 40 --stencil 27 --uniform_refine 1 "
+                  "--num_refine 1 --init_x 2 --init_y 2 --init_z 2 --max_blocks 80", 0, 2, 23),
+    "cfg1_v40": (f"--nx 10 --ny 10 --nz 10 --num_vars 40 --stencil 7 --num_refine 4 --max_blocks 4000 {SPHERE}", 0, 2, 24),
     "uni0_variable_work": ("--nx 6 --ny 4 --nz 8 --num_vars 14 --comm_vars 5 --stencil 0 --uniform_refine 1 "
                            "--num_refine 1 --init_x 2 --init_y 1 --init_z 2 --max_blocks 80", 0, 13, 19),
 }

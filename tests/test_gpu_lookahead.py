@@ -37,7 +37,8 @@ def same(g, d, m, what):
         assert not bad.any(), f"{what}: slot {s}: first {np.argwhere(bad)[0]}"
 
 
-@pytest.mark.parametrize("name", ["cfg2_like", "cfg1_like", "amr7_moved_permute", "uni27_permute", "amr7_aniso"])
+@pytest.mark.parametrize("name", ["cfg2_like", "cfg1_like", "amr7_moved_permute", "uni27_permute", "amr7_aniso",
+                                  "cfg1_v40", "cfg2_v40", "cfg5_v160"])
 def test_interleaved_stencil_and_checksum(name):
     g, d, m = pair(name)
     V = g.num_vars

@@ -47,7 +47,7 @@ def test_stage_loop_matches_golden_bit_exact(name):
 
 
 @pytest.mark.parametrize("name", ["amr7_moved_permute", "uni27_permute", "cfg3_like_ring",
-                                  "cfg2_like"])
+                                  "cfg2_like", "cfg2_v40", "cfg3_v40", "cfg5_v160"])
 def test_each_call_matches_oracle(name):
     """Finer-grained than the golden digest: compare after every comm() and every
     stencil_driver() against the oracle, so a failure names the routine."""

@@ -26,4 +26,5 @@ def test_oracle_reproduces_golden(name):
 
 def test_golden_set_is_complete():
     assert {"amr7_aniso", "amr7_moved_permute", "uni27_aniso", "uni27_permute", "cfg1_like",
-            "cfg2_like", "cfg3_like_ring", "ring27", "uni0_variable_work"} <= set(NAMES)
+            "cfg2_like", "cfg3_like_ring", "ring27", "uni0_variable_work",
+            "cfg2_v40", "cfg3_v40", "cfg5_v160", "cfg1_v40"} <= set(NAMES)

@@ -96,7 +96,7 @@ typedef struct {
 } mamr_counters;
 
 enum { MAMR_OK = 0, MAMR_ECUDA = 1, MAMR_EINVAL = 2, MAMR_EUNSUPPORTED = 3,
-       MAMR_ETOPOLOGY = 4, MAMR_ENCCL = 5 };
+       MAMR_ETOPOLOGY = 4, MAMR_ENCCL = 5, MAMR_EP2P = 6 };
 
 /* ---- lifecycle: replaces the block-array part of allocate()/deallocate(),
  *      main.c:429-450, 613-624 ------------------------------------------- */
@@ -194,6 +194,23 @@ int mamr_nccl_get_unique_id(char id[MAMR_NCCL_ID_BYTES]);   /* rank 0, then broa
 int mamr_nccl_init(mamr_ctx *ctx, const char id[MAMR_NCCL_ID_BYTES]);
 int mamr_device_count(void);        /* visible CUDA devices (0 without a driver): lets a
                                        host without CUDA headers map rank -> device */
+
+/* ---- multi-GPU without a library in the data path: peer-memory transport ----
+ * Every rank owns a window in device memory (flags, check_sum slots, the receive
+ * buffers of all comm groups).  The ranks exchange opaque handles over the host
+ * channel (MPI_Allgather in the reference's world; comm.c:71-84,120-151 posted
+ * MPI_Irecv/MPI_Isend instead) and map each other's windows: CUDA IPC between
+ * processes, plain pointers between ranks of one process (loopback tests: several
+ * contexts on one GPU, one host thread each).  From then on comm() stores ghost
+ * messages straight into the partner's receive buffer over NVLink and check_sum()
+ * all-reduces through the windows, both ordered by system-scope flags; NCCL, if
+ * initialised as well, keeps carrying migrated blocks (MAMR_TRANSPORT=nccl: everything).
+ * A peer that never answers is reported after 20 s as MAMR_EP2P by the next
+ * mamr_sync()/mamr_check_sum(), never as a hung GPU. */
+#define MAMR_P2P_HANDLE_BYTES 128
+int mamr_p2p_get_handle(mamr_ctx *ctx, char handle[MAMR_P2P_HANDLE_BYTES]);
+/* handles[num_ranks][MAMR_P2P_HANDLE_BYTES] in rank order, this rank's included */
+int mamr_p2p_connect(mamr_ctx *ctx, const char *handles);
 
 /* ---- host-only view of the halo plan (no device needed; tests and tools) --
  * The plan is what the fused stage kernel executes for one comm() call: for

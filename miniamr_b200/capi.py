@@ -65,7 +65,8 @@ EXPORTS = [
     "mamr_consolidate_block", "mamr_pack_block", "mamr_unpack_block", "mamr_send_block",
     "mamr_recv_block", "mamr_stage_send_block", "mamr_stage_recv_block", "mamr_flush_block_moves",
     "mamr_pending_block_moves", "mamr_device_count",
-    "mamr_nccl_get_unique_id", "mamr_nccl_init", "mamr_timer_begin",
+    "mamr_nccl_get_unique_id", "mamr_nccl_init", "mamr_p2p_get_handle", "mamr_p2p_connect",
+    "mamr_timer_begin",
     "mamr_timer_end", "mamr_kernel_timing", "mamr_kernel_time_ms",
     "mamr_plan_create", "mamr_plan_phase_dir", "mamr_plan_num_ops", "mamr_plan_get_ops",
     "mamr_plan_block_begin", "mamr_plan_destroy",
@@ -371,6 +372,17 @@ class DeviceMesh:
     def nccl_init(self, uid: bytes):
         assert len(uid) == 128
         self._ck(self.L.mamr_nccl_init(self.h, C.create_string_buffer(uid, 128)))
+
+    # peer-memory transport: handle out, all ranks' handles (rank order) in
+    def p2p_handle(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self._ck(self.L.mamr_p2p_get_handle(self.h, buf))
+        return buf.raw
+
+    def p2p_connect(self, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 128*self.params.num_ranks
+        self._ck(self.L.mamr_p2p_connect(self.h, C.create_string_buffer(blob, len(blob))))
 
     # ---- measurement -----------------------------------------------------------
     def counters(self):

@@ -7,6 +7,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <string>
@@ -14,6 +15,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "p2p.cuh"
 #include "stencil0.cuh"
 
 using namespace mamr;
@@ -254,6 +256,26 @@ struct mamr_ctx {
 
    ncclComm_t nccl = nullptr;
 
+   // Peer-memory transport (p2p.cu): every rank owns a window -- flags, check_sum slots and
+   // the receive buffers of all sets -- that its partners store into directly.
+   bool p2p = false;            // windows of all ranks are mapped: ghost messages and the
+                                // check_sum all-reduce go through them
+   bool p2p_inproc = false;     // some peer lives in this process (loopback): see dfree()
+   char *win = nullptr;
+   size_t win_bytes = 0, win_data_off = 0, win_data_cap = 0;   // capacity in doubles
+   std::vector<char *> peer_win;          // mapped windows, by rank (mine included)
+   std::vector<char> peer_ipc;            // opened with cudaIpcOpenMemHandle
+   char **d_peer_win = nullptr;
+   unsigned long long p2p_epoch = 0;      // mamr_set_comm_lists calls
+   unsigned long long xseq[MAX_SETS] = {};   // ghost exchanges per receive-buffer set
+   unsigned long long cs_seq = 0;         // check_sum all-reduces
+   P2PTarget *d_push[3] = {nullptr, nullptr, nullptr}, *d_credit = nullptr;
+   int n_credit = 0;
+   long long push_max[3] = {0, 0, 0};
+   unsigned *d_push_done = nullptr;
+   unsigned long long *h_p2p_err = nullptr;   // pinned
+   std::vector<void *> garbage;           // device memory whose release waits for mamr_destroy
+
    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
    bool ktiming = false;
    std::vector<EventPair> kev;
@@ -265,6 +287,8 @@ struct mamr_ctx {
 namespace {
 
 enum { KC_STENCIL = 0, KC_GHOST = 1, KC_CHECKSUM = 2 };
+
+int dfree(mamr_ctx *c, void *p);
 
 const int kPerm[6][3] = { {0, 1, 2}, {1, 2, 0}, {2, 0, 1}, {0, 2, 1}, {1, 0, 2}, {2, 1, 0} };
 
@@ -524,6 +548,60 @@ void add_unpack(mamr_ctx *c, int d, int slot, int fc, int off)
    c->ops_unpack[d].push_back(op);
 }
 
+// Peer-memory transport: lay this rank's receive buffers out in its window, publish where
+// every partner's message starts (the partner's push kernel reads the table through its
+// mapping of the window) and rebuild the push / credit lists.  Runs on every rank after
+// every mamr_set_comm_lists (build_ops).  The previous table is not read any more: every
+// push that used it was awaited by this rank before the topology could change.
+int p2p_publish(mamr_ctx *c, const size_t rneed[3])
+{
+   long long off = 0;
+   long long region[mamr_ctx::MAX_SETS][3];
+   for (int q = 0; q < c->nsets; q++)
+      for (int d = 0; d < 3; d++) {
+         region[q][d] = off;
+         off += ((long long)rneed[d] + 15)/16*16;
+      }
+   if ((size_t)off > c->win_data_cap)
+      return fail(MAMR_EP2P, "peer-memory window too small: the receive buffers of %d set(s) need %lld doubles, "
+                  "the window holds %zu (raise MAMR_P2P_WINDOW_MB)", c->nsets, off, c->win_data_cap);
+   double *data = reinterpret_cast<double *>(c->win + c->win_data_off);
+   for (int q = 0; q < c->nsets; q++)
+      for (int d = 0; d < 3; d++) c->d_recvs[q][d] = data + region[q][d];
+   // rbase[set][dir][sender]
+   std::vector<long long> rbase((size_t)P2P_MAX_SETS*3*P2P_MAX_RANKS, -1);
+   std::vector<P2PTarget> credit;
+   for (int d = 0; d < 3; d++) {
+      const DirLists &L = c->cl[d];
+      std::vector<P2PTarget> push;
+      c->push_max[d] = 0;
+      for (size_t i = 0; i < L.partner.size(); i++) {
+         for (int q = 0; q < c->nsets; q++)
+            rbase[((size_t)q*3 + d)*P2P_MAX_RANKS + L.partner[i]] = region[q][d] + L.recv_off[L.index[i]];
+         P2PTarget t;
+         t.rank = L.partner[i]; t.dir = d;
+         t.send_off = L.send_off[L.index[i]]; t.size = L.send_size[i];
+         push.push_back(t);
+         credit.push_back(t);
+         c->push_max[d] = std::max(c->push_max[d], t.size);
+      }
+      if (!push.empty())
+         CU(cudaMemcpyAsync(c->d_push[d], push.data(), push.size()*sizeof(P2PTarget), cudaMemcpyHostToDevice,
+                            c->stream));
+   }
+   c->n_credit = (int)credit.size();
+   if (!credit.empty())
+      CU(cudaMemcpyAsync(c->d_credit, credit.data(), credit.size()*sizeof(P2PTarget), cudaMemcpyHostToDevice,
+                         c->stream));
+   CU(cudaMemcpyAsync(c->win + offsetof(P2PHeader, rbase), rbase.data(), rbase.size()*sizeof(long long),
+                      cudaMemcpyHostToDevice, c->stream));
+   CU(cudaStreamSynchronize(c->stream));      // the table is in memory before the epoch says so
+   CU(cudaMemcpyAsync(c->win + offsetof(P2PHeader, epoch), &c->p2p_epoch, sizeof(unsigned long long),
+                      cudaMemcpyHostToDevice, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   return MAMR_OK;
+}
+
 // The on-rank loop of comm(), comm.c:162-203, flattened into descriptors.
 int build_ops(mamr_ctx *c)
 {
@@ -584,6 +662,7 @@ int build_ops(mamr_ctx *c)
    }
    // off-rank faces: pack + unpack descriptors from the comm lists
    c->have_partners = false;
+   size_t rneed[3] = {0, 0, 0};
    for (int d = 0; d < 3; d++) {
       const DirLists &L = c->cl[d];
       size_t smax = 0, rmax = 0;
@@ -596,27 +675,32 @@ int build_ops(mamr_ctx *c)
          smax = std::max(smax, (size_t)L.send_off[L.index[i]] + (size_t)L.send_size[i]);
          rmax = std::max(rmax, (size_t)L.recv_off[L.index[i]] + (size_t)L.recv_size[i]);
       }
+      rneed[d] = rmax;
       if (smax > c->send_cap[d]) {
-         if (c->d_send[d]) CU(cudaFree(c->d_send[d]));
+         CK(dfree(c, c->d_send[d]));
+         c->d_send[d] = nullptr;
          CU(cudaMalloc(&c->d_send[d], smax*sizeof(double)));
          CU(cudaMemsetAsync(c->d_send[d], 0, smax*sizeof(double), c->stream));
          c->send_cap[d] = smax;
       }
-      if (rmax > c->recv_cap[d]) {
+      if (!c->p2p && rmax > c->recv_cap[d]) {
          for (int q = 0; q < c->nsets; q++) {
-            if (c->d_recvs[q][d]) CU(cudaFree(c->d_recvs[q][d]));
+            CK(dfree(c, c->d_recvs[q][d]));
+            c->d_recvs[q][d] = nullptr;
             CU(cudaMalloc(&c->d_recvs[q][d], rmax*sizeof(double)));
             CU(cudaMemsetAsync(c->d_recvs[q][d], 0, rmax*sizeof(double), c->stream));
          }
          c->recv_cap[d] = rmax;
       }
    }
+   if (c->p2p) CK(p2p_publish(c, rneed));
    // upload
    size_t total = 0;
    for (int d = 0; d < 3; d++) total += c->ops_main[d].size() + c->ops_unpack[d].size();
    if (total > c->ops_cap) {
       CU(cudaStreamSynchronize(c->stream));
-      if (c->d_ops) CU(cudaFree(c->d_ops));
+      CK(dfree(c, c->d_ops));
+      c->d_ops = nullptr;
       c->ops_cap = total + total/4 + 64;
       CU(cudaMalloc(&c->d_ops, c->ops_cap*sizeof(FaceOp)));
    }
@@ -651,10 +735,76 @@ int wait_xchg(mamr_ctx *c)
    return MAMR_OK;
 }
 
-// one message per (direction, partner), comm.c:71-84 / 120-151, as NCCL send/recv
+
+// Release device memory.  cudaFree() waits for the whole device; when several ranks share
+// this process (loopback over one GPU) another rank's kernel may be spinning on a flag this
+// rank has yet to raise, so the release is put off until mamr_destroy().
+int dfree(mamr_ctx *c, void *p)
+{
+   if (!p) return MAMR_OK;
+   if (c->p2p_inproc) {
+      c->garbage.push_back(p);
+      return MAMR_OK;
+   }
+   CU(cudaFree(p));
+   return MAMR_OK;
+}
+
+// a wait of this rank's exchange kernels timed out (p2p.cu: spin_ge)?  Call after a
+// synchronisation of the stream.
+int p2p_check(mamr_ctx *c)
+{
+   if (!c->p2p) return MAMR_OK;
+   CU(cudaMemcpyAsync(c->h_p2p_err, c->win + offsetof(P2PHeader, error), sizeof(unsigned long long),
+                      cudaMemcpyDeviceToHost, c->stream));
+   CU(cudaStreamSynchronize(c->stream));
+   if (*c->h_p2p_err) {
+      const unsigned long long e = *c->h_p2p_err;
+      const char *what = (e >> 8) == 1 ? "receive-buffer credit" : (e >> 8) == 2 ? "comm-list epoch"
+                         : (e >> 8) == 3 ? "ghost message" : "check_sum contribution";
+      return fail(MAMR_EP2P, "peer-memory transport: rank %d waited %.0f s for the %s of rank %d",
+                  c->p.rank, (double)P2P_TIMEOUT_NS*1e-9, what, (int)(e & 0xff));
+   }
+   return MAMR_OK;
+}
+
+// A ghost exchange on receive-buffer set `set` begins (every rank, partners or not, once per
+// comm() call: the exchange numbers of any two ranks agree).  The consumers of the set's
+// previous contents are ahead of `st`: tell the partners that they may overwrite it.
+int p2p_begin(mamr_ctx *c, cudaStream_t st, int set)
+{
+   if (!c->p2p) return MAMR_OK;
+   ++c->xseq[set];
+   if (c->n_credit > 0) {
+      launch_p2p_credit(c->d_credit, c->n_credit, c->d_peer_win, c->p.rank, set, c->xseq[set], st);
+      c->cnt.kernel_launches++;
+   }
+   return MAMR_OK;
+}
+
+// one message per (direction, partner), comm.c:71-84 / 120-151: stores into the partners'
+// windows (p2p.cu), or NCCL send/recv
 int exchange_dir(mamr_ctx *c, int d, cudaStream_t st, int set)
 {
    const DirLists &L = c->cl[d];
+   if (c->p2p) {
+      const int np = (int)L.partner.size();
+      launch_p2p_push(c->d_push[d], np, c->push_max[d], c->d_send[d], c->d_peer_win, c->win,
+                      c->win_data_off, c->d_push_done + d*P2P_MAX_RANKS, c->p.rank, set, d, c->xseq[set],
+                      c->p2p_epoch, st);
+      launch_p2p_wait(c->d_push[d], np, c->win, set, d, c->xseq[set], st);
+      c->cnt.kernel_launches += 2;
+      for (size_t i = 0; i < L.partner.size(); i++) {
+         c->cnt.counter_halo_recv[d]++;
+         c->cnt.counter_halo_send[d]++;
+         c->cnt.size_mesg_recv[d] += (double)L.recv_size[i]*sizeof(double);
+         c->cnt.size_mesg_send[d] += (double)L.send_size[i]*sizeof(double);
+         c->cnt.counter_face_send[d] += L.num[i];
+         c->cnt.counter_face_recv[d] += L.num[i];
+      }
+      CU(cudaGetLastError());
+      return MAMR_OK;
+   }
    NC(g_nccl.GroupStart());
    for (size_t i = 0; i < L.partner.size(); i++) {
       NC(g_nccl.Recv(c->d_recvs[set][d] + L.recv_off[L.index[i]], (size_t)L.recv_size[i], NCCL_DOUBLE,
@@ -672,35 +822,43 @@ int exchange_dir(mamr_ctx *c, int d, cudaStream_t st, int set)
    return MAMR_OK;
 }
 
-// Execute one direction-phased comm() on variables [start, start+num) in place in
-// their current pool (all in the same pool): the split path.  buf_var0 is the
-// first variable of the comm() call (variable 0 of the message buffers); with
-// exchange == false the receive buffers already hold this call's messages.
+// Execute one direction-phased comm() on variables [start, start+num) in place in their
+// current pools: the split path.  buf_var0 is the first variable of the comm() call
+// (variable 0 of the message buffers); with exchange == false the receive buffers already
+// hold this call's messages.  Exactly one exchange per direction, however the variables
+// are spread over the two pools (every rank issues the same number of exchanges).
 int comm_split(mamr_ctx *c, int start, int num, int ord, int buf_var0, bool exchange, int set)
 {
    if (c->ops_dirty) CK(build_ops(c));
-   if (c->have_partners && !c->nccl)
-      return fail(MAMR_ENCCL, "comm: off-rank partners present but mamr_nccl_init was not called");
+   if (c->have_partners && !c->nccl && !c->p2p)
+      return fail(MAMR_ENCCL, "comm: off-rank partners present but neither mamr_p2p_connect nor "
+                  "mamr_nccl_init was called");
    CK(wait_xchg(c));
-   double *pool = vpool(c, start);
+   if (exchange) CK(p2p_begin(c, c->stream, set));
+   const std::vector<Run> runs = runs_of(c, start, num, false);
    for (int o = 0; o < 3; o++) {
       const int d = kPerm[ord][o];
       const DirLists &L = c->cl[d];
-      if (!c->ops_main[d].empty() && num > 0) {
-         KTimer t(c, KC_GHOST);
-         launch_ghost(c->d_ops + c->off_main[d], (int)c->ops_main[d].size(), pool, c->d_send[d],
-                      c->d_recvs[set][d], c->g.var_stride, start, num, buf_var0, c->stream);
-         c->cnt.kernel_launches++;
-      }
-      if (!L.partner.empty()) {
-         if (exchange) CK(exchange_dir(c, d, c->stream, set));
-         if (!c->ops_unpack[d].empty() && num > 0) {
+      if (!c->ops_main[d].empty())
+         for (const Run &r : runs) {
             KTimer t(c, KC_GHOST);
-            launch_ghost(c->d_ops + c->off_unpack[d], (int)c->ops_unpack[d].size(), pool,
-                         c->d_send[d], c->d_recvs[set][d], c->g.var_stride, start, num, buf_var0,
-                         c->stream);
+            launch_ghost(c->d_ops + c->off_main[d], (int)c->ops_main[d].size(), vpool(c, r.start), c->d_send[d],
+                         c->d_recvs[set][d], c->g.var_stride, r.start, r.num, buf_var0, c->stream);
             c->cnt.kernel_launches++;
          }
+      if (!L.partner.empty()) {
+         if (exchange) {
+            KTimer t(c, KC_GHOST);
+            CK(exchange_dir(c, d, c->stream, set));
+         }
+         if (!c->ops_unpack[d].empty())
+            for (const Run &r : runs) {
+               KTimer t(c, KC_GHOST);
+               launch_ghost(c->d_ops + c->off_unpack[d], (int)c->ops_unpack[d].size(), vpool(c, r.start),
+                            c->d_send[d], c->d_recvs[set][d], c->g.var_stride, r.start, r.num, buf_var0,
+                            c->stream);
+               c->cnt.kernel_launches++;
+            }
       }
    }
    CU(cudaGetLastError());
@@ -755,7 +913,7 @@ int build_slab_plan(mamr_ctx *c, int ord)
 {
    const HaloPlan &P = c->plan[ord];
    for (void *p : { (void *)c->d_fsrc[ord], (void *)c->d_cops[ord], (void *)c->d_cbegin[ord] })
-      if (p) CU(cudaFree(p));
+      CK(dfree(c, p));
    c->d_fsrc[ord] = nullptr; c->d_cops[ord] = nullptr; c->d_cbegin[ord] = nullptr;
    c->slab_ok[ord] = false;
    if (!c->slab_geom || !c->use_slab || !c->use_elide || c->p.stencil != 7 || !P.ok || !P.elidable)
@@ -845,8 +1003,8 @@ int ensure_plan(mamr_ctx *c, int ord)
    c->plan_built[ord] = true;
    if (!P.ok) return MAMR_OK;
    CU(cudaStreamSynchronize(c->stream));
-   if (c->d_hops[ord]) CU(cudaFree(c->d_hops[ord]));
-   if (c->d_hbegin[ord]) CU(cudaFree(c->d_hbegin[ord]));
+   CK(dfree(c, c->d_hops[ord]));
+   CK(dfree(c, c->d_hbegin[ord]));
    c->d_hops[ord] = nullptr;
    c->d_hbegin[ord] = nullptr;
    CU(cudaMalloc(&c->d_hops[ord], std::max<size_t>(1, P.ops.size())*sizeof(BoxOp)));
@@ -858,14 +1016,14 @@ int ensure_plan(mamr_ctx *c, int ord)
                       cudaMemcpyHostToDevice, c->stream));
    // eliding launches: identity ops that the stencil does not read are dropped
    // (7-point: everything but the faces)
-   if (c->d_lops[ord]) CU(cudaFree(c->d_lops[ord]));
-   if (c->d_lbegin[ord]) CU(cudaFree(c->d_lbegin[ord]));
+   CK(dfree(c, c->d_lops[ord]));
+   CK(dfree(c, c->d_lbegin[ord]));
    c->d_lops[ord] = nullptr;
    c->d_lbegin[ord] = nullptr;
    c->plan_has_ident[ord] = false;
    for (const BoxOp &op : P.ops)
       if (op.flags & BF_IDENT) c->plan_has_ident[ord] = true;
-   if (c->d_zsrc[ord]) CU(cudaFree(c->d_zsrc[ord]));
+   CK(dfree(c, c->d_zsrc[ord]));
    c->d_zsrc[ord] = nullptr;
    if (P.elidable && c->fused2_geom) {
       std::vector<BoxOp> lean;
@@ -914,7 +1072,7 @@ int ensure_plan(mamr_ctx *c, int ord)
    }
    CK(build_slab_plan(c, ord));
    // interior blocks (no halo cell out of a receive buffer) first, boundary blocks last
-   if (c->d_order_ord[ord]) CU(cudaFree(c->d_order_ord[ord]));
+   CK(dfree(c, c->d_order_ord[ord]));
    c->d_order_ord[ord] = nullptr;
    c->n_interior[ord] = 0;
    if (c->have_partners && c->use_overlap && c->num_active > 0 &&
@@ -934,7 +1092,7 @@ int ensure_plan(mamr_ctx *c, int ord)
       CU(cudaStreamSynchronize(c->stream));
    }
    for (int o = 0; o < 3; o++) {
-      if (c->d_pack[ord][o]) CU(cudaFree(c->d_pack[ord][o]));
+      CK(dfree(c, c->d_pack[ord][o]));
       c->d_pack[ord][o] = nullptr;
       const std::vector<BoxOp> &K = c->pack[ord][o];
       if (!c->have_partners || K.empty()) continue;
@@ -951,7 +1109,7 @@ int fused_ready(mamr_ctx *c, int ord, bool *yes)
 {
    *yes = false;
    if (!c->use_fused || !(c->fused_geom || c->slab_geom) || c->num_active == 0) return MAMR_OK;
-   if (c->have_partners && !c->nccl) return MAMR_OK;   // comm_split reports the error
+   if (c->have_partners && !c->nccl && !c->p2p) return MAMR_OK;   // comm_split reports the error
    CK(ensure_plan(c, ord));
    *yes = c->plan[ord].ok && (c->fused_geom || c->slab_ok[ord]);
    return MAMR_OK;
@@ -1017,7 +1175,7 @@ int run_stencil0(mamr_ctx *c, int pool, int v0, int n)
    const int mat = c->s0_mat, kind = c->pend_stage%6;
    if (c->s0_work_blocks < c->num_active && kind >= S0_SEVEN) {
       CU(cudaStreamSynchronize(c->stream));
-      if (c->d_s0_work) CU(cudaFree(c->d_s0_work));
+      CK(dfree(c, c->d_s0_work));
       c->d_s0_work = nullptr;
       CU(cudaMalloc(&c->d_s0_work, (size_t)c->p.max_blocks*c->g.tile_stride*sizeof(double)));
       c->s0_work_blocks = c->p.max_blocks;
@@ -1495,8 +1653,18 @@ void mamr_destroy(mamr_ctx *c)
    cudaFree(c->d_ops);
    for (int d = 0; d < 3; d++) {
       cudaFree(c->d_send[d]);
-      for (int q = 0; q < mamr_ctx::MAX_SETS; q++) cudaFree(c->d_recvs[q][d]);
+      if (!c->p2p)      // with the peer-memory transport they are part of the window
+         for (int q = 0; q < mamr_ctx::MAX_SETS; q++) cudaFree(c->d_recvs[q][d]);
+      cudaFree(c->d_push[d]);
    }
+   for (size_t r = 0; r < c->peer_win.size(); r++)
+      if (c->peer_ipc[r]) cudaIpcCloseMemHandle(c->peer_win[r]);
+   cudaFree(c->win);
+   cudaFree(c->d_peer_win);
+   cudaFree(c->d_credit);
+   cudaFree(c->d_push_done);
+   if (c->h_p2p_err) cudaFreeHost(c->h_p2p_err);
+   for (void *g : c->garbage) cudaFree(g);
    cudaFree(c->d_partials);
    cudaFree(c->d_cspart);
    cudaFree(c->d_sums);
@@ -1538,6 +1706,7 @@ int mamr_sync(mamr_ctx *c)
    CK(wait_xchg(c));
    CU(cudaStreamSynchronize(c->stream));
    if (c->xstream) CU(cudaStreamSynchronize(c->xstream));
+   CK(p2p_check(c));
    CK(fold_s0_checks(c));
    return MAMR_OK;
 }
@@ -1683,7 +1852,7 @@ int mamr_upload_interiors(mamr_ctx *c, int var_start, int num, int num_slots, co
       CU(cudaStreamSynchronize(c->stream));
       CU(cudaStreamSynchronize(c->upstream));
       for (int b = 0; b < 2; b++) {
-         if (c->d_up[b]) CU(cudaFree(c->d_up[b]));
+         CK(dfree(c, c->d_up[b]));
          c->d_up[b] = nullptr;
          CU(cudaMalloc(&c->d_up[b], (size_t)S*per_slot*sizeof(double)));
          c->up_fill_rec[b] = false;
@@ -1765,15 +1934,15 @@ int mamr_set_topology(mamr_ctx *c, int num_active, const mamr_block *sorted_bloc
    c->num_active = num_active;
    if ((size_t)num_active > c->slots_cap) {
       CU(cudaStreamSynchronize(c->stream));
-      if (c->d_slots) CU(cudaFree(c->d_slots));
-      if (c->d_order) CU(cudaFree(c->d_order));
+      CK(dfree(c, c->d_slots));
+      CK(dfree(c, c->d_order));
       c->slots_cap = (size_t)num_active + num_active/4 + 64;
       CU(cudaMalloc(&c->d_slots, c->slots_cap*sizeof(int)));
       CU(cudaMalloc(&c->d_order, c->slots_cap*sizeof(int)));
    }
    if ((size_t)num_active*c->p.num_vars > c->partials_cap) {
       CU(cudaStreamSynchronize(c->stream));
-      if (c->d_partials) CU(cudaFree(c->d_partials));
+      CK(dfree(c, c->d_partials));
       c->partials_cap = c->slots_cap*c->p.num_vars;
       CU(cudaMalloc(&c->d_partials, c->partials_cap*sizeof(double)));
    }
@@ -1781,7 +1950,7 @@ int mamr_set_topology(mamr_ctx *c, int num_active, const mamr_block *sorted_bloc
       // the fused kernels' check_sum partials: CS_WARPS slots per tile-variable, zero where
       // a kernel has fewer compute warps
       CU(cudaStreamSynchronize(c->stream));
-      if (c->d_cspart) CU(cudaFree(c->d_cspart));
+      CK(dfree(c, c->d_cspart));
       c->d_cspart = nullptr;
       c->cspart_cap = c->partials_cap;
       CU(cudaMalloc(&c->d_cspart, c->cspart_cap*CS_WARPS*sizeof(double)));
@@ -1809,6 +1978,7 @@ int mamr_set_comm_lists(mamr_ctx *c, const mamr_comm_dir dirs[3])
 {
    if (!c || !dirs) return fail(MAMR_EINVAL, "null argument");
    CK(settle_all(c));
+   c->p2p_epoch++;      // every rank calls this at the same program point (p2p.cu: rbase table)
    for (int o = 0; o < 6; o++) c->plan_built[o] = false;
    for (int d = 0; d < 3; d++) {
       const mamr_comm_dir &s = dirs[d];
@@ -1867,6 +2037,7 @@ int mamr_comm(mamr_ctx *c, int start, int num_comm, int stage)
    if (defer) {
       // the fused kernel performs this exchange when the stencil of the variables
       // is launched; anything else that needs the ghost cells materialises it
+      if (!c->have_partners && num_comm > 0) CK(p2p_begin(c, c->stream, set));   // exchange numbers stay aligned
       if (c->have_partners && num_comm > 0) {
          // this group's receive buffers are about to be reused: whatever else still
          // reads them (another group mapped to the same set) becomes real first
@@ -1884,6 +2055,7 @@ int mamr_comm(mamr_ctx *c, int start, int num_comm, int stage)
             CU(cudaEventRecord(c->ev_data, c->stream));
             CU(cudaStreamWaitEvent(xs, c->ev_data, 0));
          }
+         CK(p2p_begin(c, xs, set));
          for (int o = 0; o < 3; o++) {
             const int d = kPerm[ord][o];
             if (c->cl[d].partner.empty()) continue;
@@ -1894,7 +2066,10 @@ int mamr_comm(mamr_ctx *c, int start, int num_comm, int stage)
                              xs);
                c->cnt.kernel_launches++;
             }
-            CK(exchange_dir(c, d, xs, set));
+            {
+               KTimer t(c, KC_GHOST, xs);
+               CK(exchange_dir(c, d, xs, set));
+            }
          }
          if (c->use_overlap) {
             CU(cudaEventRecord(c->ev_xchg, xs));
@@ -1909,8 +2084,7 @@ int mamr_comm(mamr_ctx *c, int start, int num_comm, int stage)
       }
    } else {
       if (c->have_partners && num_comm > 0) CK(release_recv_set(c, set));
-      for (const Run &r : runs_of(c, start, num_comm, false))
-         CK(comm_split(c, r.start, r.num, ord, start, true, set));
+      if (num_comm > 0) CK(comm_split(c, start, num_comm, ord, start, true, set));
    }
    for (int d = 0; d < 3; d++) {
       c->cnt.counter_same[d] += c->n_same[d];
@@ -2032,14 +2206,22 @@ int mamr_check_sum_vars(mamr_ctx *c, int var_start, int num, double *sums)
       }
    }
    CU(cudaGetLastError());
-   if (c->p.num_ranks > 1) {
-      if (!c->nccl) return fail(MAMR_ENCCL, "check_sum: mamr_nccl_init was not called");
-      NC(g_nccl.AllReduce(c->d_sums, c->d_sums, (size_t)num, NCCL_DOUBLE, NCCL_SUM, c->nccl,
-                          c->stream));   // check_sum.c:57
+   if (c->p.num_ranks > 1) {      // check_sum.c:57
+      if (c->p2p) {
+         KTimer t(c, KC_CHECKSUM);
+         launch_p2p_allreduce(c->d_sums, num, c->d_peer_win, c->win, c->p.rank, c->p.num_ranks,
+                              c->p.num_vars, ++c->cs_seq, c->stream);
+         c->cnt.kernel_launches++;
+      } else {
+         if (!c->nccl)
+            return fail(MAMR_ENCCL, "check_sum: neither mamr_p2p_connect nor mamr_nccl_init was called");
+         NC(g_nccl.AllReduce(c->d_sums, c->d_sums, (size_t)num, NCCL_DOUBLE, NCCL_SUM, c->nccl, c->stream));
+      }
    }
    CU(cudaMemcpyAsync(c->h_sums, c->d_sums, (num + extra)*sizeof(double), cudaMemcpyDeviceToHost,
                       c->stream));
    CU(cudaStreamSynchronize(c->stream));
+   if (c->p.num_ranks > 1) CK(p2p_check(c));
    CK(fold_s0_checks(c));
    for (int i = 0; i < extra; i++) {
       c->spec_cs[var_start + num + i] = c->h_sums[num + i];
@@ -2239,7 +2421,7 @@ int grow_stage(mamr_ctx *c, double **buf, size_t *cap, size_t need, size_t keep)
    if (*buf && keep)
       CU(cudaMemcpyAsync(nb, *buf, keep*n*sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
    CU(cudaStreamSynchronize(c->stream));
-   if (*buf) CU(cudaFree(*buf));
+   CK(dfree(c, *buf));
    *buf = nb;
    *cap = ncap;
    return MAMR_OK;
@@ -2345,6 +2527,114 @@ int mamr_nccl_init(mamr_ctx *c, const char id[MAMR_NCCL_ID_BYTES])
    ncclUniqueId u;
    memcpy(u.internal, id, MAMR_NCCL_ID_BYTES);
    NC(g_nccl.CommInitRank(&c->nccl, c->p.num_ranks, u, c->p.rank));
+   return MAMR_OK;
+}
+
+// ---- peer-memory transport (p2p.cu) -------------------------------------------
+namespace {
+struct P2PBlob {            // what travels over the host channel, MAMR_P2P_HANDLE_BYTES
+   unsigned long long magic;
+   long long pid;
+   unsigned long long ptr;          // the window's address in the owner's process
+   unsigned long long bytes;
+   int device, num_vars;
+   cudaIpcMemHandle_t ipc;
+};
+static_assert(sizeof(P2PBlob) <= MAMR_P2P_HANDLE_BYTES, "handle blob too big");
+constexpr unsigned long long P2P_MAGIC = 0x6d616d7270327031ULL;
+}  // namespace
+
+int mamr_p2p_get_handle(mamr_ctx *c, char handle[MAMR_P2P_HANDLE_BYTES])
+{
+   if (!c || !handle) return fail(MAMR_EINVAL, "null argument");
+   if (c->p.num_ranks > P2P_MAX_RANKS)
+      return fail(MAMR_EUNSUPPORTED, "peer-memory transport: at most %d ranks (one node)", P2P_MAX_RANKS);
+   if (!c->win) {
+      // window = header + check_sum slots + receive buffers of every set.  Default capacity:
+      // a sixteenth of one block pool (the ghost layer of a sub-cube of b^3 blocks of n^3 cells
+      // is 6/(b n) of it per variable group), at least 64 MB; MAMR_P2P_WINDOW_MB overrides.
+      size_t data = std::max<size_t>((size_t)64 << 20, c->pool_bytes/16);
+      if (const char *e = getenv("MAMR_P2P_WINDOW_MB")) data = (size_t)atoll(e) << 20;
+      c->win_data_off = p2p_data_offset(c->p.num_vars);
+      c->win_data_cap = data/sizeof(double);
+      c->win_bytes = c->win_data_off + data;
+      CU(cudaMalloc(&c->win, c->win_bytes));
+      CU(cudaMemsetAsync(c->win, 0, c->win_bytes, c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+   }
+   P2PBlob b;
+   memset(&b, 0, sizeof b);
+   b.magic = P2P_MAGIC;
+   b.pid = (long long)getpid();
+   b.ptr = (unsigned long long)(uintptr_t)c->win;
+   b.bytes = c->win_bytes;
+   b.num_vars = c->p.num_vars;
+   CU(cudaGetDevice(&b.device));
+   CU(cudaIpcGetMemHandle(&b.ipc, c->win));
+   memset(handle, 0, MAMR_P2P_HANDLE_BYTES);
+   memcpy(handle, &b, sizeof b);
+   return MAMR_OK;
+}
+
+int mamr_p2p_connect(mamr_ctx *c, const char *handles)
+{
+   if (!c || !handles) return fail(MAMR_EINVAL, "null argument");
+   if (!c->win) return fail(MAMR_EINVAL, "p2p_connect: call mamr_p2p_get_handle first");
+   if (c->p2p) return fail(MAMR_EINVAL, "p2p_connect: already connected");
+   const int R = c->p.num_ranks;
+   CK(settle_all(c));
+   c->peer_win.assign(R, nullptr);
+   c->peer_ipc.assign(R, 0);
+   for (int r = 0; r < R; r++) {
+      P2PBlob b;
+      memcpy(&b, handles + (size_t)r*MAMR_P2P_HANDLE_BYTES, sizeof b);
+      if (b.magic != P2P_MAGIC || b.num_vars != c->p.num_vars)
+         return fail(MAMR_EINVAL, "p2p_connect: handle of rank %d is not a window of this job", r);
+      if (r == c->p.rank) {
+         if ((char *)(uintptr_t)b.ptr != c->win) return fail(MAMR_EINVAL, "p2p_connect: handle %d is not mine", r);
+         c->peer_win[r] = c->win;
+      } else if (b.pid == (long long)getpid()) {
+         // a rank of this process (loopback): same address space.  Another device needs
+         // peer access; the same device needs nothing.
+         int dev = 0;
+         CU(cudaGetDevice(&dev));
+         if (b.device != dev) {
+            cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+               return fail(MAMR_ECUDA, "p2p_connect: no peer access from device %d to %d: %s", dev, b.device,
+                           cudaGetErrorString(e));
+            cudaGetLastError();
+         }
+         c->peer_win[r] = (char *)(uintptr_t)b.ptr;
+         c->p2p_inproc = true;
+      } else {
+         void *q = nullptr;
+         CU(cudaIpcOpenMemHandle(&q, b.ipc, cudaIpcMemLazyEnablePeerAccess));
+         c->peer_win[r] = (char *)q;
+         c->peer_ipc[r] = 1;
+      }
+   }
+   CU(cudaMalloc(&c->d_peer_win, (size_t)R*sizeof(char *)));
+   CU(cudaMemcpy(c->d_peer_win, c->peer_win.data(), (size_t)R*sizeof(char *), cudaMemcpyHostToDevice));
+   for (int d = 0; d < 3; d++) CU(cudaMalloc(&c->d_push[d], (size_t)P2P_MAX_RANKS*sizeof(P2PTarget)));
+   CU(cudaMalloc(&c->d_credit, (size_t)3*P2P_MAX_RANKS*sizeof(P2PTarget)));
+   CU(cudaMalloc(&c->d_push_done, (size_t)3*P2P_MAX_RANKS*sizeof(unsigned)));
+   CU(cudaMemset(c->d_push_done, 0, (size_t)3*P2P_MAX_RANKS*sizeof(unsigned)));
+   CU(cudaMallocHost(&c->h_p2p_err, sizeof(unsigned long long)));
+   *c->h_p2p_err = 0;
+   // receive buffers allocated for another transport move into the window at the next comm()
+   for (int d = 0; d < 3; d++) {
+      for (int q = 0; q < mamr_ctx::MAX_SETS; q++) {
+         if (c->d_recvs[q][d]) CU(cudaFree(c->d_recvs[q][d]));
+         c->d_recvs[q][d] = nullptr;
+      }
+      c->recv_cap[d] = 0;
+   }
+   c->p2p = true;
+   if (const char *e = getenv("MAMR_TRANSPORT"))
+      if (!strcmp(e, "nccl") && c->nccl) c->p2p = false;     // keep NCCL for A/B measurements
+   c->ops_dirty = true;
+   for (int o = 0; o < 6; o++) c->plan_built[o] = false;
    return MAMR_OK;
 }
 

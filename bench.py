@@ -290,11 +290,18 @@ def run_ours(args):
                        num_ranks=world)
         d.set_topology(top["slots"], top["level"], top["nei_level"], top["nei"])
         if world > 1:
-            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-            if rank == 0:
-                uid.copy_(torch.frombuffer(bytearray(DeviceMesh.nccl_unique_id()), dtype=torch.uint8))
-            dist.broadcast(uid, 0)
-            d.nccl_init(bytes(uid.cpu().numpy().tobytes()))
+            if args.transport == "nccl":
+                uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+                if rank == 0:
+                    uid.copy_(torch.frombuffer(bytearray(DeviceMesh.nccl_unique_id()), dtype=torch.uint8))
+                dist.broadcast(uid, 0)
+                d.nccl_init(bytes(uid.cpu().numpy().tobytes()))
+            else:
+                # peer-memory transport: ghost faces are stored straight into the partner's receive
+                # buffers over NVLink (windows mapped with CUDA IPC; handles over the host channel)
+                hs = [None]*world
+                dist.all_gather_object(hs, d.p2p_handle())
+                d.p2p_connect(hs)
             d.set_comm_lists(top["dirs"])
         # synthetic state in pinned host memory, as init.c:484-495 defines it: interiors only
         # (the ghost layer starts at zero), [slot][var][nx][ny][nz] = block payloads back to back
@@ -476,6 +483,9 @@ def run_ours(args):
                                                   "the stage kernel, folded and read back), device-resident"},
             "gpu_launches": int(cnt["kernel_launches"]),
             "nvlink_bytes_per_step": (sum(cnt["size_mesg_send"])/args.steps if world > 1 else 0),
+            "transport": (None if world == 1 else
+                          "peer-memory stores + system-scope flags (p2p.cu)" if args.transport == "p2p"
+                          else "ncclSend/ncclRecv"),
             "checksum_drift": drift,
         }
     d.close()
@@ -532,6 +542,8 @@ def main():
     ap.add_argument("--blocks", type=int, default=0, help="blocks per edge per GPU (default per workload)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--transport", default=os.environ.get("MAMR_TRANSPORT", "p2p"), choices=["p2p", "nccl"],
+                    help="N > 1: ghost exchange by stores into peer memory (default) or NCCL send/recv")
     ap.add_argument("--no-also", action="store_true", help="skip the cfg3 / cfg1 device-resident legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -43,7 +43,8 @@ static int topo_dirty = 1;      /* device descriptors older than blocks[]/comm l
 static int host_fresh = 1;      /* blocks[].array holds data the device has not seen */
 static mamr_counters seen;      /* counters already added to the reference's globals */
 static double *stage_tile;      /* one block, [var][i][j][k] contiguous            */
-static int nccl_moves;          /* migrated block payloads travel GPU to GPU (NCCL)   */
+static int nccl_moves;          /* migrated block payloads travel GPU to GPU (peer
+                                   memory or NCCL) instead of through send_buff      */
 
 static void die(const char *where)
 {
@@ -87,12 +88,25 @@ static void ensure_ctx(void)
    }
    OK(mamr_create(&p, &G), "create");
    if (num_pes > 1) {
-      /* the NCCL id travels over the host channel, like every other piece of metadata */
-      char id[MAMR_NCCL_ID_BYTES];
-      memset(id, 0, sizeof id);
-      if (!my_pe) OK(mamr_nccl_get_unique_id(id), "nccl_get_unique_id");
-      MPI_Bcast(id, MAMR_NCCL_ID_BYTES, MPI_CHAR, 0, MPI_COMM_WORLD);
-      OK(mamr_nccl_init(G, id), "nccl_init");
+      const char *tr = getenv("MAMR_TRANSPORT");       /* "p2p" (default) | "nccl" */
+      if (tr && !strcmp(tr, "nccl")) {
+         /* the NCCL id travels over the host channel, like every other piece of metadata */
+         char id[MAMR_NCCL_ID_BYTES];
+         memset(id, 0, sizeof id);
+         if (!my_pe) OK(mamr_nccl_get_unique_id(id), "nccl_get_unique_id");
+         MPI_Bcast(id, MAMR_NCCL_ID_BYTES, MPI_CHAR, 0, MPI_COMM_WORLD);
+         OK(mamr_nccl_init(G, id), "nccl_init");
+      } else {
+         /* peer-memory transport: every rank's window handle to every rank -- an all-gather,
+            spelled with the one collective of miniAMR's MPI subset that combines buffers */
+         int words = MAMR_P2P_HANDLE_BYTES/(int) sizeof(int), n = num_pes*words;
+         int *mine = (int *) calloc((size_t) n, sizeof(int)), *all = (int *) calloc((size_t) n, sizeof(int));
+         OK(mamr_p2p_get_handle(G, (char *)(mine + my_pe*words)), "p2p_get_handle");
+         MPI_Allreduce(mine, all, n, MPI_INT, MPI_SUM, MPI_COMM_WORLD);
+         OK(mamr_p2p_connect(G, (const char *) all), "p2p_connect");
+         free(mine);
+         free(all);
+      }
       nccl_moves = !(getenv("MAMR_HOST_MIGRATION") && atoi(getenv("MAMR_HOST_MIGRATION")));
    }
    stage_tile = (double *) malloc((size_t)num_vars*tile_doubles()*sizeof(double));

@@ -10,6 +10,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <set>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -274,7 +275,17 @@ struct mamr_ctx {
    long long push_max[3] = {0, 0, 0};
    unsigned *d_push_done = nullptr;
    unsigned long long *h_p2p_err = nullptr;   // pinned
-   std::vector<void *> garbage;           // device memory whose release waits for mamr_destroy
+   std::set<void *> async_allocs;         // dalloc(): stream-ordered allocations
+   std::vector<void *> garbage;           // release put off until mamr_destroy (dfree)
+   // migrated blocks over the windows (pull): staged payloads + their (dest, ordinal) table live
+   // in the sender's window from win_mv_off on; mv_seq counts mamr_flush_block_moves calls
+   size_t win_mv_off = 0;
+   int mv_cap_p2p = 0;
+   unsigned long long mv_seq = 0;
+   P2PMove *d_mv_moves = nullptr;
+   int *d_mv_k = nullptr, *d_mv_ranks = nullptr;
+   unsigned char *d_cur = nullptr;
+   size_t mv_moves_cap = 0;
 
    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
    bool ktiming = false;
@@ -289,6 +300,7 @@ namespace {
 enum { KC_STENCIL = 0, KC_GHOST = 1, KC_CHECKSUM = 2 };
 
 int dfree(mamr_ctx *c, void *p);
+template <typename T> int dalloc(mamr_ctx *c, T **p, size_t bytes);
 
 const int kPerm[6][3] = { {0, 1, 2}, {1, 2, 0}, {2, 0, 1}, {0, 2, 1}, {1, 0, 2}, {2, 1, 0} };
 
@@ -679,7 +691,7 @@ int build_ops(mamr_ctx *c)
       if (smax > c->send_cap[d]) {
          CK(dfree(c, c->d_send[d]));
          c->d_send[d] = nullptr;
-         CU(cudaMalloc(&c->d_send[d], smax*sizeof(double)));
+         CK(dalloc(c, &c->d_send[d], smax*sizeof(double)));
          CU(cudaMemsetAsync(c->d_send[d], 0, smax*sizeof(double), c->stream));
          c->send_cap[d] = smax;
       }
@@ -687,7 +699,7 @@ int build_ops(mamr_ctx *c)
          for (int q = 0; q < c->nsets; q++) {
             CK(dfree(c, c->d_recvs[q][d]));
             c->d_recvs[q][d] = nullptr;
-            CU(cudaMalloc(&c->d_recvs[q][d], rmax*sizeof(double)));
+            CK(dalloc(c, &c->d_recvs[q][d], rmax*sizeof(double)));
             CU(cudaMemsetAsync(c->d_recvs[q][d], 0, rmax*sizeof(double), c->stream));
          }
          c->recv_cap[d] = rmax;
@@ -702,7 +714,7 @@ int build_ops(mamr_ctx *c)
       CK(dfree(c, c->d_ops));
       c->d_ops = nullptr;
       c->ops_cap = total + total/4 + 64;
-      CU(cudaMalloc(&c->d_ops, c->ops_cap*sizeof(FaceOp)));
+      CK(dalloc(c, &c->d_ops, c->ops_cap*sizeof(FaceOp)));
    }
    std::vector<FaceOp> all;
    all.reserve(total);
@@ -736,17 +748,27 @@ int wait_xchg(mamr_ctx *c)
 }
 
 
-// Release device memory.  cudaFree() waits for the whole device; when several ranks share
-// this process (loopback over one GPU) another rank's kernel may be spinning on a flag this
-// rank has yet to raise, so the release is put off until mamr_destroy().
+// Device memory for descriptors and staging areas that come and go with the topology.
+// cudaMalloc() and cudaFree() may wait for the whole device; when several ranks share this
+// process (loopback over one GPU) another rank's kernel may be spinning on a flag this rank has
+// yet to raise, so there both are stream-ordered on the main stream instead (which has waited
+// for the exchange and boundary streams whenever descriptors are replaced).
+template <typename T> int dalloc(mamr_ctx *c, T **p, size_t bytes)
+{
+   if (c->p2p_inproc) {
+      CU(cudaMallocAsync((void **)p, bytes, c->stream));
+      c->async_allocs.insert((void *)*p);
+   } else
+      CU(cudaMalloc((void **)p, bytes));
+   return MAMR_OK;
+}
+
 int dfree(mamr_ctx *c, void *p)
 {
    if (!p) return MAMR_OK;
-   if (c->p2p_inproc) {
-      c->garbage.push_back(p);
-      return MAMR_OK;
-   }
-   CU(cudaFree(p));
+   if (c->async_allocs.erase(p)) CU(cudaFreeAsync(p, c->stream));
+   else if (c->p2p_inproc) c->garbage.push_back(p);     // allocated before the windows were connected
+   else CU(cudaFree(p));
    return MAMR_OK;
 }
 
@@ -761,7 +783,8 @@ int p2p_check(mamr_ctx *c)
    if (*c->h_p2p_err) {
       const unsigned long long e = *c->h_p2p_err;
       const char *what = (e >> 8) == 1 ? "receive-buffer credit" : (e >> 8) == 2 ? "comm-list epoch"
-                         : (e >> 8) == 3 ? "ghost message" : "check_sum contribution";
+                         : (e >> 8) == 3 ? "ghost message" : (e >> 8) == 4 ? "check_sum contribution"
+                         : (e >> 8) == 5 ? "migrated-block table" : "migration acknowledgement";
       return fail(MAMR_EP2P, "peer-memory transport: rank %d waited %.0f s for the %s of rank %d",
                   c->p.rank, (double)P2P_TIMEOUT_NS*1e-9, what, (int)(e & 0xff));
    }
@@ -966,9 +989,9 @@ int build_slab_plan(mamr_ctx *c, int ord)
       if ((int)cops.size() - cbegin[a] > slab7_max_cell_ops()) return MAMR_OK;
    }
    cbegin[nb] = (int)cops.size();
-   CU(cudaMalloc(&c->d_fsrc[ord], fsrc.size()*sizeof(long long)));
-   CU(cudaMalloc(&c->d_cops[ord], std::max<size_t>(1, cops.size())*sizeof(BoxOp)));
-   CU(cudaMalloc(&c->d_cbegin[ord], cbegin.size()*sizeof(int)));
+   CK(dalloc(c, &c->d_fsrc[ord], fsrc.size()*sizeof(long long)));
+   CK(dalloc(c, &c->d_cops[ord], std::max<size_t>(1, cops.size())*sizeof(BoxOp)));
+   CK(dalloc(c, &c->d_cbegin[ord], cbegin.size()*sizeof(int)));
    CU(cudaMemcpyAsync(c->d_fsrc[ord], fsrc.data(), fsrc.size()*sizeof(long long),
                       cudaMemcpyHostToDevice, c->stream));
    if (!cops.empty())
@@ -1007,8 +1030,8 @@ int ensure_plan(mamr_ctx *c, int ord)
    CK(dfree(c, c->d_hbegin[ord]));
    c->d_hops[ord] = nullptr;
    c->d_hbegin[ord] = nullptr;
-   CU(cudaMalloc(&c->d_hops[ord], std::max<size_t>(1, P.ops.size())*sizeof(BoxOp)));
-   CU(cudaMalloc(&c->d_hbegin[ord], P.begin.size()*sizeof(int)));
+   CK(dalloc(c, &c->d_hops[ord], std::max<size_t>(1, P.ops.size())*sizeof(BoxOp)));
+   CK(dalloc(c, &c->d_hbegin[ord], P.begin.size()*sizeof(int)));
    if (!P.ops.empty())
       CU(cudaMemcpyAsync(c->d_hops[ord], P.ops.data(), P.ops.size()*sizeof(BoxOp),
                          cudaMemcpyHostToDevice, c->stream));
@@ -1058,14 +1081,14 @@ int ensure_plan(mamr_ctx *c, int ord)
          }
       }
       lbegin[P.begin.size() - 1] = (int)lean.size();
-      CU(cudaMalloc(&c->d_lops[ord], std::max<size_t>(1, lean.size())*sizeof(BoxOp)));
-      CU(cudaMalloc(&c->d_lbegin[ord], lbegin.size()*sizeof(int)));
+      CK(dalloc(c, &c->d_lops[ord], std::max<size_t>(1, lean.size())*sizeof(BoxOp)));
+      CK(dalloc(c, &c->d_lbegin[ord], lbegin.size()*sizeof(int)));
       if (!lean.empty())
          CU(cudaMemcpyAsync(c->d_lops[ord], lean.data(), lean.size()*sizeof(BoxOp),
                             cudaMemcpyHostToDevice, c->stream));
       CU(cudaMemcpyAsync(c->d_lbegin[ord], lbegin.data(), lbegin.size()*sizeof(int),
                          cudaMemcpyHostToDevice, c->stream));
-      CU(cudaMalloc(&c->d_zsrc[ord], zsrc.size()*sizeof(long long)));
+      CK(dalloc(c, &c->d_zsrc[ord], zsrc.size()*sizeof(long long)));
       CU(cudaMemcpyAsync(c->d_zsrc[ord], zsrc.data(), zsrc.size()*sizeof(long long),
                          cudaMemcpyHostToDevice, c->stream));
       CU(cudaStreamSynchronize(c->stream));   // the host vectors go out of scope
@@ -1086,7 +1109,7 @@ int ensure_plan(mamr_ctx *c, int ord)
       for (int a : c->h_order) if (!bnd[a]) ordv.push_back(a);
       c->n_interior[ord] = (int)ordv.size();
       for (int a : c->h_order) if (bnd[a]) ordv.push_back(a);
-      CU(cudaMalloc(&c->d_order_ord[ord], ordv.size()*sizeof(int)));
+      CK(dalloc(c, &c->d_order_ord[ord], ordv.size()*sizeof(int)));
       CU(cudaMemcpyAsync(c->d_order_ord[ord], ordv.data(), ordv.size()*sizeof(int),
                          cudaMemcpyHostToDevice, c->stream));
       CU(cudaStreamSynchronize(c->stream));
@@ -1096,7 +1119,7 @@ int ensure_plan(mamr_ctx *c, int ord)
       c->d_pack[ord][o] = nullptr;
       const std::vector<BoxOp> &K = c->pack[ord][o];
       if (!c->have_partners || K.empty()) continue;
-      CU(cudaMalloc(&c->d_pack[ord][o], K.size()*sizeof(BoxOp)));
+      CK(dalloc(c, &c->d_pack[ord][o], K.size()*sizeof(BoxOp)));
       CU(cudaMemcpyAsync(c->d_pack[ord][o], K.data(), K.size()*sizeof(BoxOp),
                          cudaMemcpyHostToDevice, c->stream));
    }
@@ -1177,7 +1200,7 @@ int run_stencil0(mamr_ctx *c, int pool, int v0, int n)
       CU(cudaStreamSynchronize(c->stream));
       CK(dfree(c, c->d_s0_work));
       c->d_s0_work = nullptr;
-      CU(cudaMalloc(&c->d_s0_work, (size_t)c->p.max_blocks*c->g.tile_stride*sizeof(double)));
+      CK(dalloc(c, &c->d_s0_work, (size_t)c->p.max_blocks*c->g.tile_stride*sizeof(double)));
       c->s0_work_blocks = c->p.max_blocks;
    }
    int v = v0;
@@ -1481,6 +1504,89 @@ void touch_all(mamr_ctx *c, bool uniform = false)
    std::fill(c->zf_ok.begin(), c->zf_ok.end(), 0);
 }
 
+// mamr_flush_block_moves over the windows.  Sender: table (destination, ordinal among the sends
+// to that destination) next to the payloads it staged, then the ready flag.  Receiver: look
+// its receives up in the senders' tables, fetch the payloads straight into the tiles, tell the
+// senders.  The sender's staging area is free again when every destination has said so.
+int p2p_flush_moves(mamr_ctx *c)
+{
+   ++c->mv_seq;
+   if (c->mv_send.empty() && c->mv_recv.empty()) return MAMR_OK;
+   CK(settle_all(c));
+   const int R = c->p.num_ranks;
+   std::vector<int> ranks;
+   if (!c->mv_send.empty()) {
+      const int ns = (int)c->mv_send.size();
+      std::vector<int> tab((size_t)2*c->mv_cap_p2p, -1), per(R, 0);
+      for (int k = 0; k < ns; k++) {
+         tab[k] = c->mv_send[k].peer;
+         tab[c->mv_cap_p2p + k] = per[c->mv_send[k].peer]++;
+      }
+      CU(cudaMemcpyAsync(c->win + c->win_mv_off, tab.data(), (size_t)ns*sizeof(int), cudaMemcpyHostToDevice,
+                         c->stream));
+      CU(cudaMemcpyAsync(c->win + c->win_mv_off + (size_t)c->mv_cap_p2p*sizeof(int), tab.data() + c->mv_cap_p2p,
+                         (size_t)ns*sizeof(int), cudaMemcpyHostToDevice, c->stream));
+      const unsigned long long cnt = (unsigned long long)ns;
+      CU(cudaMemcpyAsync(c->win + offsetof(P2PHeader, mv_count), &cnt, sizeof cnt, cudaMemcpyHostToDevice,
+                         c->stream));
+      CU(cudaStreamSynchronize(c->stream));      // payloads, table and count are in memory ...
+      CU(cudaMemcpyAsync(c->win + offsetof(P2PHeader, mv_ready), &c->mv_seq, sizeof c->mv_seq,
+                         cudaMemcpyHostToDevice, c->stream));                      // ... before the flag says so
+   }
+   if (!c->mv_recv.empty()) {
+      const int nr = (int)c->mv_recv.size();
+      if ((size_t)nr > c->mv_moves_cap) {
+         CK(dfree(c, c->d_mv_moves));
+         CK(dfree(c, c->d_mv_k));
+         c->d_mv_moves = nullptr; c->d_mv_k = nullptr;
+         c->mv_moves_cap = (size_t)nr + nr/2 + 16;
+         CK(dalloc(c, &c->d_mv_moves, c->mv_moves_cap*sizeof(P2PMove)));
+         CK(dalloc(c, &c->d_mv_k, c->mv_moves_cap*sizeof(int)));
+      }
+      std::vector<P2PMove> mv(nr);
+      std::vector<int> per(R, 0);
+      std::vector<char> isrc(R, 0);
+      for (int i = 0; i < nr; i++) {
+         mv[i].slot = c->mv_recv[i].slot;
+         mv[i].src = c->mv_recv[i].peer;
+         mv[i].ordinal = per[mv[i].src]++;
+         mv[i].pad = 0;
+         isrc[mv[i].src] = 1;
+      }
+      for (int r = 0; r < R; r++) if (isrc[r]) ranks.push_back(r);
+      CU(cudaMemcpyAsync(c->d_mv_moves, mv.data(), (size_t)nr*sizeof(P2PMove), cudaMemcpyHostToDevice, c->stream));
+      CU(cudaMemcpyAsync(c->d_cur, c->cur.data(), (size_t)c->p.num_vars, cudaMemcpyHostToDevice, c->stream));
+      CU(cudaMemcpyAsync(c->d_mv_ranks, ranks.data(), ranks.size()*sizeof(int), cudaMemcpyHostToDevice, c->stream));
+      CU(cudaStreamSynchronize(c->stream));      // the host vectors go out of scope
+      launch_p2p_mv_resolve(c->d_mv_moves, nr, c->d_peer_win, c->win, c->win_mv_off, c->mv_cap_p2p, c->p.rank,
+                            c->mv_seq, c->d_mv_k, c->stream);
+      launch_p2p_mv_unpack(c->d_mv_moves, nr, c->d_mv_k, c->d_peer_win, c->win_mv_off, c->mv_cap_p2p, c->pool[0],
+                           c->pool[1], c->d_cur, c->p.nx, c->p.ny, c->p.nz, c->g.tile_stride, c->g.var_stride,
+                           c->p.num_vars, c->stream);
+      launch_p2p_mv_done(c->d_mv_ranks, (int)ranks.size(), c->d_peer_win, c->p.rank, c->mv_seq, c->stream);
+      c->cnt.kernel_launches += 3;
+   }
+   if (!c->mv_send.empty()) {
+      // my staging area is reused by the next load-balance step: every destination has fetched
+      std::vector<char> isdst(R, 0);
+      std::vector<int> dsts;
+      for (const mamr_ctx::MoveRec &m : c->mv_send) isdst[m.peer] = 1;
+      for (int r = 0; r < R; r++) if (isdst[r]) dsts.push_back(r);
+      CU(cudaMemcpyAsync(c->d_mv_ranks + P2P_MAX_RANKS, dsts.data(), dsts.size()*sizeof(int), cudaMemcpyHostToDevice,
+                         c->stream));
+      CU(cudaStreamSynchronize(c->stream));
+      launch_p2p_mv_wait(c->d_mv_ranks + P2P_MAX_RANKS, (int)dsts.size(), c->win, c->mv_seq, c->stream);
+      c->cnt.kernel_launches++;
+   }
+   CU(cudaGetLastError());
+   const size_t n = (size_t)c->p.num_vars*c->p.nx*c->p.ny*c->p.nz;
+   c->cnt.migrate_bytes += (double)c->mv_send.size()*n*sizeof(double);
+   if (!c->mv_recv.empty()) touch_all(c, true);
+   c->mv_send.clear();
+   c->mv_recv.clear();
+   return MAMR_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -1663,8 +1769,13 @@ void mamr_destroy(mamr_ctx *c)
    cudaFree(c->d_peer_win);
    cudaFree(c->d_credit);
    cudaFree(c->d_push_done);
+   cudaFree(c->d_mv_moves);
+   cudaFree(c->d_mv_k);
+   cudaFree(c->d_mv_ranks);
+   cudaFree(c->d_cur);
    if (c->h_p2p_err) cudaFreeHost(c->h_p2p_err);
    for (void *g : c->garbage) cudaFree(g);
+
    cudaFree(c->d_partials);
    cudaFree(c->d_cspart);
    cudaFree(c->d_sums);
@@ -1854,7 +1965,7 @@ int mamr_upload_interiors(mamr_ctx *c, int var_start, int num, int num_slots, co
       for (int b = 0; b < 2; b++) {
          CK(dfree(c, c->d_up[b]));
          c->d_up[b] = nullptr;
-         CU(cudaMalloc(&c->d_up[b], (size_t)S*per_slot*sizeof(double)));
+         CK(dalloc(c, &c->d_up[b], (size_t)S*per_slot*sizeof(double)));
          c->up_fill_rec[b] = false;
       }
       c->up_cap = (size_t)S*per_slot;
@@ -1908,6 +2019,7 @@ int mamr_set_topology(mamr_ctx *c, int num_active, const mamr_block *sorted_bloc
    if (num_active > c->p.max_blocks)
       return fail(MAMR_EINVAL, "num_active %d > max_blocks %d", num_active, c->p.max_blocks);
    CK(settle_all(c));
+   CK(wait_xchg(c));
    for (int a = 0; a < num_active; a++)
       if (sorted_blocks[a].slot < 0 || sorted_blocks[a].slot >= c->p.max_blocks)
          return fail(MAMR_EINVAL, "active block %d has slot %d out of range", a, sorted_blocks[a].slot);
@@ -1937,14 +2049,14 @@ int mamr_set_topology(mamr_ctx *c, int num_active, const mamr_block *sorted_bloc
       CK(dfree(c, c->d_slots));
       CK(dfree(c, c->d_order));
       c->slots_cap = (size_t)num_active + num_active/4 + 64;
-      CU(cudaMalloc(&c->d_slots, c->slots_cap*sizeof(int)));
-      CU(cudaMalloc(&c->d_order, c->slots_cap*sizeof(int)));
+      CK(dalloc(c, &c->d_slots, c->slots_cap*sizeof(int)));
+      CK(dalloc(c, &c->d_order, c->slots_cap*sizeof(int)));
    }
    if ((size_t)num_active*c->p.num_vars > c->partials_cap) {
       CU(cudaStreamSynchronize(c->stream));
       CK(dfree(c, c->d_partials));
       c->partials_cap = c->slots_cap*c->p.num_vars;
-      CU(cudaMalloc(&c->d_partials, c->partials_cap*sizeof(double)));
+      CK(dalloc(c, &c->d_partials, c->partials_cap*sizeof(double)));
    }
    if (c->partials_cap != c->cspart_cap) {
       // the fused kernels' check_sum partials: CS_WARPS slots per tile-variable, zero where
@@ -1953,7 +2065,7 @@ int mamr_set_topology(mamr_ctx *c, int num_active, const mamr_block *sorted_bloc
       CK(dfree(c, c->d_cspart));
       c->d_cspart = nullptr;
       c->cspart_cap = c->partials_cap;
-      CU(cudaMalloc(&c->d_cspart, c->cspart_cap*CS_WARPS*sizeof(double)));
+      CK(dalloc(c, &c->d_cspart, c->cspart_cap*CS_WARPS*sizeof(double)));
       CU(cudaMemsetAsync(c->d_cspart, 0, c->cspart_cap*CS_WARPS*sizeof(double), c->stream));
    }
    std::vector<int> slots(num_active);
@@ -1978,6 +2090,7 @@ int mamr_set_comm_lists(mamr_ctx *c, const mamr_comm_dir dirs[3])
 {
    if (!c || !dirs) return fail(MAMR_EINVAL, "null argument");
    CK(settle_all(c));
+   CK(wait_xchg(c));
    c->p2p_epoch++;      // every rank calls this at the same program point (p2p.cu: rbase table)
    for (int o = 0; o < 6; o++) c->plan_built[o] = false;
    for (int d = 0; d < 3; d++) {
@@ -2431,7 +2544,8 @@ int grow_stage(mamr_ctx *c, double **buf, size_t *cap, size_t need, size_t keep)
 int mamr_stage_send_block(mamr_ctx *c, int slot, int dest_rank)
 {
    CK(check_slot(c, slot));
-   if (!c->nccl) return fail(MAMR_ENCCL, "stage_send_block: mamr_nccl_init was not called");
+   if (!c->nccl && !c->p2p)
+      return fail(MAMR_ENCCL, "stage_send_block: neither mamr_p2p_connect nor mamr_nccl_init was called");
    if (dest_rank < 0 || dest_rank >= c->p.num_ranks || dest_rank == c->p.rank)
       return fail(MAMR_EINVAL, "stage_send_block: bad destination rank %d", dest_rank);
    for (const mamr_ctx::MoveRec &r : c->mv_recv)
@@ -2439,8 +2553,18 @@ int mamr_stage_send_block(mamr_ctx *c, int slot, int dest_rank)
          return fail(MAMR_EINVAL, "stage_send_block: slot %d still waits for its own payload", slot);
    CK(flush_pending(c));
    const size_t n = (size_t)c->p.num_vars*c->p.nx*c->p.ny*c->p.nz;
-   CK(grow_stage(c, &c->d_mv_send, &c->mv_send_cap, c->mv_send.size() + 1, c->mv_send.size()));
-   double *dst = c->d_mv_send + c->mv_send.size()*n;
+   double *dst;
+   if (c->p2p) {
+      // peer-memory transport: the payload waits in this rank's window for the receiver to fetch it
+      if ((int)c->mv_send.size() >= c->mv_cap_p2p)
+         return fail(MAMR_EP2P, "more than %d blocks leave this rank in one load-balance step: raise "
+                     "MAMR_P2P_MOVE_BLOCKS", c->mv_cap_p2p);
+      dst = reinterpret_cast<double *>(c->win + c->win_mv_off + p2p_mv_payload_offset(c->mv_cap_p2p)) +
+            c->mv_send.size()*n;
+   } else {
+      CK(grow_stage(c, &c->d_mv_send, &c->mv_send_cap, c->mv_send.size() + 1, c->mv_send.size()));
+      dst = c->d_mv_send + c->mv_send.size()*n;
+   }
    for (const Run &r : runs_of(c, 0, c->p.num_vars, false)) {
       launch_pack_block(vpool(c, r.start), c->g, slot, r.start, r.num, dst, c->stream);
       c->cnt.kernel_launches++;
@@ -2453,7 +2577,8 @@ int mamr_stage_send_block(mamr_ctx *c, int slot, int dest_rank)
 int mamr_stage_recv_block(mamr_ctx *c, int slot, int src_rank)
 {
    CK(check_slot(c, slot));
-   if (!c->nccl) return fail(MAMR_ENCCL, "stage_recv_block: mamr_nccl_init was not called");
+   if (!c->nccl && !c->p2p)
+      return fail(MAMR_ENCCL, "stage_recv_block: neither mamr_p2p_connect nor mamr_nccl_init was called");
    if (src_rank < 0 || src_rank >= c->p.num_ranks || src_rank == c->p.rank)
       return fail(MAMR_EINVAL, "stage_recv_block: bad source rank %d", src_rank);
    for (const mamr_ctx::MoveRec &r : c->mv_recv)
@@ -2478,6 +2603,7 @@ int mamr_flush_block_moves(mamr_ctx *c)
       std::fill(c->cs_local_dirty.begin(), c->cs_local_dirty.end(), 0);
       c->modified_since_cs = true;
    }
+   if (c->p2p) return p2p_flush_moves(c);
    if (c->mv_send.empty() && c->mv_recv.empty()) return MAMR_OK;
    if (!c->nccl) return fail(MAMR_ENCCL, "flush_block_moves: mamr_nccl_init was not called");
    CK(settle_all(c));
@@ -2557,7 +2683,13 @@ int mamr_p2p_get_handle(mamr_ctx *c, char handle[MAMR_P2P_HANDLE_BYTES])
       if (const char *e = getenv("MAMR_P2P_WINDOW_MB")) data = (size_t)atoll(e) << 20;
       c->win_data_off = p2p_data_offset(c->p.num_vars);
       c->win_data_cap = data/sizeof(double);
-      c->win_bytes = c->win_data_off + data;
+      // migration staging: room for half of the pool's slots, at most 2 GB (MAMR_P2P_MOVE_BLOCKS)
+      const size_t pay = (size_t)c->p.num_vars*c->p.nx*c->p.ny*c->p.nz*sizeof(double);
+      size_t mvb = std::max<size_t>(8, std::min<size_t>((size_t)c->p.max_blocks/2, ((size_t)2 << 30)/pay));
+      if (const char *e = getenv("MAMR_P2P_MOVE_BLOCKS")) mvb = (size_t)std::max(1, atoi(e));
+      c->mv_cap_p2p = (int)std::min<size_t>(mvb, (size_t)c->p.max_blocks);
+      c->win_mv_off = (c->win_data_off + data + 255)/256*256;
+      c->win_bytes = c->win_mv_off + p2p_mv_payload_offset(c->mv_cap_p2p) + (size_t)c->mv_cap_p2p*pay;
       CU(cudaMalloc(&c->win, c->win_bytes));
       CU(cudaMemsetAsync(c->win, 0, c->win_bytes, c->stream));
       CU(cudaStreamSynchronize(c->stream));
@@ -2606,6 +2738,13 @@ int mamr_p2p_connect(mamr_ctx *c, const char *handles)
             cudaGetLastError();
          }
          c->peer_win[r] = (char *)(uintptr_t)b.ptr;
+         if (!c->p2p_inproc) {
+            // stream-ordered allocations (dalloc) never hand memory back to the driver
+            cudaMemPool_t pool;
+            unsigned long long keep = ~0ULL;
+            CU(cudaDeviceGetDefaultMemPool(&pool, dev));
+            CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+         }
          c->p2p_inproc = true;
       } else {
          void *q = nullptr;
@@ -2622,6 +2761,12 @@ int mamr_p2p_connect(mamr_ctx *c, const char *handles)
    CU(cudaMemset(c->d_push_done, 0, (size_t)3*P2P_MAX_RANKS*sizeof(unsigned)));
    CU(cudaMallocHost(&c->h_p2p_err, sizeof(unsigned long long)));
    *c->h_p2p_err = 0;
+   CU(cudaMalloc(&c->d_mv_ranks, (size_t)2*P2P_MAX_RANKS*sizeof(int)));
+   // (sized for every slot: no allocation while a peer may be spinning on this rank)
+   c->mv_moves_cap = (size_t)c->p.max_blocks;
+   CU(cudaMalloc(&c->d_mv_moves, c->mv_moves_cap*sizeof(P2PMove)));
+   CU(cudaMalloc(&c->d_mv_k, c->mv_moves_cap*sizeof(int)));
+   CU(cudaMalloc(&c->d_cur, (size_t)c->p.num_vars));
    // receive buffers allocated for another transport move into the window at the next comm()
    for (int d = 0; d < 3; d++) {
       for (int q = 0; q < mamr_ctx::MAX_SETS; q++) {

@@ -157,7 +157,96 @@ p2p_allreduce_kernel(double *sums, int num, char *const *peer, char *mine_raw, i
    }
 }
 
+// ---- block migration: pull -------------------------------------------------------
+// The sender has packed its outgoing blocks into its window and written, per staged block,
+// the destination rank and the ordinal among its sends to that rank.  The receiver's k-th
+// staged receive from rank S is S's k-th staged send to it (rcb.c:207-337 moves blocks of one
+// pair in order).
+__global__ void __launch_bounds__(256)
+p2p_mv_resolve_kernel(const P2PMove *recvs, char *const *peer, char *mine_raw, size_t mv_off, int mv_cap,
+                      int me, unsigned long long seq, int *k_out)
+{
+   const P2PMove R = recvs[blockIdx.x];
+   P2PHeader *mine = reinterpret_cast<P2PHeader *>(mine_raw);
+   P2PHeader *H = reinterpret_cast<P2PHeader *>(peer[R.src]);
+   __shared__ int s_ok;
+   if (threadIdx.x == 0) {
+      k_out[blockIdx.x] = -1;
+      s_ok = spin_ge(&H->mv_ready, seq, mine, 0x500ULL | (unsigned)R.src) ? 1 : 0;
+   }
+   __syncthreads();
+   if (!s_ok) return;
+   const int count = (int)ld_acquire_sys(&H->mv_count);
+   const volatile int *dest = reinterpret_cast<const volatile int *>(peer[R.src] + mv_off);
+   const volatile int *ord = dest + mv_cap;
+   for (int k = threadIdx.x; k < count; k += blockDim.x)
+      if (dest[k] == me && ord[k] == R.ordinal) k_out[blockIdx.x] = k;
+}
+
+// grid = (receives, variables)
+__global__ void __launch_bounds__(256)
+p2p_mv_unpack_kernel(const P2PMove *recvs, const int *k_in, char *const *peer, size_t pay_off,
+                     double *pool0, double *pool1, const unsigned char *cur, int nx, int ny, int nz,
+                     long long tile_stride, long long var_stride, int num_vars)
+{
+   const P2PMove R = recvs[blockIdx.x];
+   const int k = k_in[blockIdx.x];
+   if (k < 0) return;
+   const int var = blockIdx.y;
+   const int sj = nz + 2, si = (ny + 2)*sj, cells = nx*ny*nz;
+   const double *pl = reinterpret_cast<const double *>(peer[R.src] + pay_off) +
+                      ((size_t)k*num_vars + var)*cells;
+   double *tile = (cur[var] ? pool1 : pool0) + (long long)var*var_stride + (long long)R.slot*tile_stride;
+   for (int c = threadIdx.x; c < cells; c += blockDim.x) {
+      const int i = c/(ny*nz), r = c - i*ny*nz, j = r/nz, kk = r - j*nz;
+      tile[(size_t)(i + 1)*si + (j + 1)*sj + (kk + 1)] = pl[c];
+   }
+}
+
+__global__ void p2p_mv_done_kernel(const int *ranks, int n, char *const *peer, int me, unsigned long long seq)
+{
+   for (int t = threadIdx.x; t < n; t += blockDim.x)
+      st_release_sys(&reinterpret_cast<P2PHeader *>(peer[ranks[t]])->mv_done[me], seq);
+}
+
+__global__ void p2p_mv_wait_kernel(const int *ranks, int n, char *mine_raw, unsigned long long seq)
+{
+   P2PHeader *mine = reinterpret_cast<P2PHeader *>(mine_raw);
+   for (int t = threadIdx.x; t < n; t += blockDim.x)
+      spin_ge(&mine->mv_done[ranks[t]], seq, mine, 0x600ULL | (unsigned)ranks[t]);
+}
+
 }  // namespace
+
+void launch_p2p_mv_resolve(const P2PMove *d_recvs, int n, char *const *d_peer, char *mine, size_t mv_off,
+                           int mv_cap, int me, unsigned long long seq, int *d_k, cudaStream_t s)
+{
+   if (n <= 0) return;
+   p2p_mv_resolve_kernel<<<n, 256, 0, s>>>(d_recvs, d_peer, mine, mv_off, mv_cap, me, seq, d_k);
+}
+
+void launch_p2p_mv_unpack(const P2PMove *d_recvs, int n, const int *d_k, char *const *d_peer, size_t mv_off,
+                          int mv_cap, double *pool0, double *pool1, const unsigned char *d_cur, int nx, int ny,
+                          int nz, long long tile_stride, long long var_stride, int num_vars, cudaStream_t s)
+{
+   if (n <= 0) return;
+   dim3 grid((unsigned)n, (unsigned)num_vars);
+   p2p_mv_unpack_kernel<<<grid, 256, 0, s>>>(d_recvs, d_k, d_peer, mv_off + p2p_mv_payload_offset(mv_cap), pool0,
+                                             pool1, d_cur, nx, ny, nz, tile_stride, var_stride, num_vars);
+}
+
+void launch_p2p_mv_done(const int *d_ranks, int n, char *const *d_peer, int me, unsigned long long seq,
+                        cudaStream_t s)
+{
+   if (n <= 0) return;
+   p2p_mv_done_kernel<<<1, 64, 0, s>>>(d_ranks, n, d_peer, me, seq);
+}
+
+void launch_p2p_mv_wait(const int *d_ranks, int n, char *mine, unsigned long long seq, cudaStream_t s)
+{
+   if (n <= 0) return;
+   p2p_mv_wait_kernel<<<1, 64, 0, s>>>(d_ranks, n, mine, seq);
+}
 
 void launch_p2p_credit(const P2PTarget *d_targets, int n, char *const *d_peer, int me, int set,
                        unsigned long long seq, cudaStream_t s)

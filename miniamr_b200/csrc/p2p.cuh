@@ -20,6 +20,10 @@ struct P2PHeader {
    long long rbase[P2P_MAX_SETS][3][P2P_MAX_RANKS];
    // check_sum all-reduce: [buffer][contributor]
    unsigned long long cs_flag[2][P2P_MAX_RANKS];
+   // block migration (pull): the owner's staged payloads and their table are complete for
+   // move round mv_ready (mv_count entries); mv_done[puller]: `puller` has fetched its share
+   unsigned long long mv_ready, mv_count;
+   unsigned long long mv_done[P2P_MAX_RANKS];
 };
 
 // byte offsets inside a window: header | check_sum values [2][P2P_MAX_RANKS][max_vars] | data
@@ -34,6 +38,27 @@ struct P2PTarget {
    int rank, dir;
    long long send_off, size;       // push: the message inside my send buffer (doubles)
 };
+
+// one staged receive of a migrated block: the `ordinal`-th block rank `src` sends to me
+struct P2PMove {
+   int slot, src, ordinal, pad;
+};
+
+// Migration area of a window (byte offset mv_off): int dest[mv_cap], int ordinal[mv_cap], then
+// the staged payloads (pack.c:66-70 layout) from p2p_mv_payload_offset() on.
+inline size_t p2p_mv_payload_offset(int mv_cap) { return ((size_t)2*mv_cap*sizeof(int) + 255)/256*256; }
+
+// find the staging index of every staged receive in its sender's table (waits for the sender)
+void launch_p2p_mv_resolve(const P2PMove *d_recvs, int n, char *const *d_peer, char *mine, size_t mv_off,
+                           int mv_cap, int me, unsigned long long seq, int *d_k, cudaStream_t s);
+// fetch the payloads from the senders' windows straight into the tiles' interiors
+void launch_p2p_mv_unpack(const P2PMove *d_recvs, int n, const int *d_k, char *const *d_peer, size_t mv_off,
+                          int mv_cap, double *pool0, double *pool1, const unsigned char *d_cur, int nx, int ny,
+                          int nz, long long tile_stride, long long var_stride, int num_vars, cudaStream_t s);
+// tell the senders (ranks[0..n)) that their payloads have been fetched / wait for my pullers
+void launch_p2p_mv_done(const int *d_ranks, int n, char *const *d_peer, int me, unsigned long long seq,
+                        cudaStream_t s);
+void launch_p2p_mv_wait(const int *d_ranks, int n, char *mine, unsigned long long seq, cudaStream_t s);
 
 void launch_p2p_credit(const P2PTarget *d_targets, int n, char *const *d_peer, int me, int set,
                        unsigned long long seq, cudaStream_t s);

@@ -45,11 +45,17 @@ def main():
     d = DeviceMesh(nx, ny, nz, V, nb, stencil=stencil, comm_vars=comm_vars, permute=permute,
                    device=local, rank=rank, num_ranks=world)
     d.set_topology(top["slots"], top["level"], top["nei_level"], top["nei"])
-    uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        uid.copy_(torch.frombuffer(bytearray(DeviceMesh.nccl_unique_id()), dtype=torch.uint8))
-    dist.broadcast(uid, 0)
-    d.nccl_init(bytes(uid.cpu().numpy().tobytes()))
+    if os.environ.get("MAMR_TRANSPORT", "p2p") == "nccl":
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(DeviceMesh.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        d.nccl_init(bytes(uid.cpu().numpy().tobytes()))
+    else:
+        # peer-memory transport: window handles all-gathered over the host channel (CUDA IPC)
+        hs = [None]*world
+        dist.all_gather_object(hs, d.p2p_handle())
+        d.p2p_connect(hs)
     d.set_comm_lists(top["dirs"])
     rx, ry, rz = rank_coords(rank, npx, npy, npz)
     for s in range(nb):

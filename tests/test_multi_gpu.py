@@ -59,3 +59,20 @@ def test_two_ranks_match_single_rank_oracle(case, fused):
            os.path.join(ROOT, "tests", "mgpu_worker.py"), json.dumps(cfg)]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("case", [4, 6, 8, 12, 14])
+def test_nccl_transport_matches_single_rank_oracle(case):
+    """the same through ncclSend/ncclRecv and ncclAllReduce (MAMR_TRANSPORT=nccl) instead of the
+    peer-memory transport"""
+    cfg = CASES[case]
+    world = cfg["np"][0]*cfg["np"][1]*cfg["np"][2]
+    if ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ)
+    env["MAMR_TRANSPORT"] = "nccl"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+           "--master-addr", "127.0.0.1", "--master-port", str(29700 + case),
+           os.path.join(ROOT, "tests", "mgpu_worker.py"), json.dumps(cfg)]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MGPU_OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -29,7 +29,10 @@ def oracle_from_golden(g):
     return m
 
 
-@pytest.mark.parametrize("name", [n for n in NAMES if n not in ("cfg3_like_ring", "ring27")])
+# (the *_v40 / *_v160 fixtures share their topologies with cfg1_like / cfg2_like; the plan does not
+# depend on the number of variables, and the numpy executor would take minutes on them)
+@pytest.mark.parametrize("name", [n for n in NAMES if n not in ("cfg3_like_ring", "ring27", "cfg1_v40", "cfg2_v40",
+                                                                "cfg3_v40", "cfg5_v160")])
 def test_plan_equals_three_phase_comm(name):
     g = Golden(name)
     m = oracle_from_golden(g)

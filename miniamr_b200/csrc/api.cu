@@ -10,7 +10,7 @@
 #include <unistd.h>
 
 #include <algorithm>
-#include <set>
+#include <map>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -275,7 +275,10 @@ struct mamr_ctx {
    long long push_max[3] = {0, 0, 0};
    unsigned *d_push_done = nullptr;
    unsigned long long *h_p2p_err = nullptr;   // pinned
-   std::set<void *> async_allocs;         // dalloc(): stream-ordered allocations
+   char *arena = nullptr;                 // dalloc(): ranks sharing a process
+   size_t arena_cap = 0, arena_top = 0;
+   std::map<void *, size_t> arena_size;
+   std::multimap<size_t, void *> arena_free;
    std::vector<void *> garbage;           // release put off until mamr_destroy (dfree)
    // migrated blocks over the windows (pull): staged payloads + their (dest, ordinal) table live
    // in the sender's window from win_mv_off on; mv_seq counts mamr_flush_block_moves calls
@@ -749,25 +752,42 @@ int wait_xchg(mamr_ctx *c)
 
 
 // Device memory for descriptors and staging areas that come and go with the topology.
-// cudaMalloc() and cudaFree() may wait for the whole device; when several ranks share this
-// process (loopback over one GPU) another rank's kernel may be spinning on a flag this rank has
-// yet to raise, so there both are stream-ordered on the main stream instead (which has waited
-// for the exchange and boundary streams whenever descriptors are replaced).
+// cudaMalloc() and cudaFree() (and a stream-ordered pool that has to grow) may wait for the
+// whole device; when several ranks share this process (loopback over one GPU) another rank's
+// kernel may be spinning on a flag this rank has yet to raise.  There the memory comes out of
+// an arena set aside when the windows are connected: bump allocation plus a free list by size;
+// a block is reused in stream order on the main stream, which has waited for the exchange and
+// boundary streams whenever descriptors are replaced.
 template <typename T> int dalloc(mamr_ctx *c, T **p, size_t bytes)
 {
-   if (c->p2p_inproc) {
-      CU(cudaMallocAsync((void **)p, bytes, c->stream));
-      c->async_allocs.insert((void *)*p);
-   } else
-      CU(cudaMalloc((void **)p, bytes));
+   if (c->arena) {
+      const size_t sz = (std::max<size_t>(bytes, 1) + 255)/256*256;
+      auto it = c->arena_free.lower_bound(sz);
+      if (it != c->arena_free.end() && it->first <= 2*sz) {
+         *p = (T *)it->second;
+         c->arena_free.erase(it);
+         return MAMR_OK;
+      }
+      if (c->arena_top + sz <= c->arena_cap) {
+         *p = (T *)(c->arena + c->arena_top);
+         c->arena_size[(void *)*p] = sz;
+         c->arena_top += sz;
+         return MAMR_OK;
+      }
+      static bool warned = false;
+      if (!warned) fprintf(stderr, "miniamr_b200: in-process arena exhausted (MAMR_INPROC_ARENA_MB); falling back to cudaMalloc\n");
+      warned = true;
+   }
+   CU(cudaMalloc((void **)p, bytes));
    return MAMR_OK;
 }
 
 int dfree(mamr_ctx *c, void *p)
 {
    if (!p) return MAMR_OK;
-   if (c->async_allocs.erase(p)) CU(cudaFreeAsync(p, c->stream));
-   else if (c->p2p_inproc) c->garbage.push_back(p);     // allocated before the windows were connected
+   auto it = c->arena_size.find(p);
+   if (it != c->arena_size.end()) c->arena_free.insert({ it->second, p });
+   else if (c->p2p_inproc) c->garbage.push_back(p);     // cudaMalloc'ed: release put off until mamr_destroy
    else CU(cudaFree(p));
    return MAMR_OK;
 }
@@ -1730,6 +1750,11 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
    return MAMR_OK;
 }
 
+static void xfree(mamr_ctx *c, void *p)      // arena blocks go with the arena
+{
+   if (p && !c->arena_size.count(p)) cudaFree(p);
+}
+
 void mamr_destroy(mamr_ctx *c)
 {
    if (!c) return;
@@ -1739,61 +1764,62 @@ void mamr_destroy(mamr_ctx *c)
    drain_ktimers(c);
    for (cudaEvent_t e : c->ev_free) cudaEventDestroy(e);
    if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
-   cudaFree(c->pool[0]);
-   cudaFree(c->pool[1]);
-   cudaFree(c->zf[0]);
-   cudaFree(c->zf[1]);
+   xfree(c, c->pool[0]);
+   xfree(c, c->pool[1]);
+   xfree(c, c->zf[0]);
+   xfree(c, c->zf[1]);
    for (int o = 0; o < 6; o++) {
-      cudaFree(c->d_hops[o]);
-      cudaFree(c->d_hbegin[o]);
-      cudaFree(c->d_lops[o]);
-      cudaFree(c->d_lbegin[o]);
-      cudaFree(c->d_zsrc[o]);
-      cudaFree(c->d_fsrc[o]);
-      cudaFree(c->d_cops[o]);
-      cudaFree(c->d_cbegin[o]);
-      for (int q = 0; q < 3; q++) cudaFree(c->d_pack[o][q]);
+      xfree(c, c->d_hops[o]);
+      xfree(c, c->d_hbegin[o]);
+      xfree(c, c->d_lops[o]);
+      xfree(c, c->d_lbegin[o]);
+      xfree(c, c->d_zsrc[o]);
+      xfree(c, c->d_fsrc[o]);
+      xfree(c, c->d_cops[o]);
+      xfree(c, c->d_cbegin[o]);
+      for (int q = 0; q < 3; q++) xfree(c, c->d_pack[o][q]);
    }
-   cudaFree(c->d_slots);
-   cudaFree(c->d_order);
-   cudaFree(c->d_ops);
+   xfree(c, c->d_slots);
+   xfree(c, c->d_order);
+   xfree(c, c->d_ops);
    for (int d = 0; d < 3; d++) {
-      cudaFree(c->d_send[d]);
+      xfree(c, c->d_send[d]);
       if (!c->p2p)      // with the peer-memory transport they are part of the window
-         for (int q = 0; q < mamr_ctx::MAX_SETS; q++) cudaFree(c->d_recvs[q][d]);
-      cudaFree(c->d_push[d]);
+         for (int q = 0; q < mamr_ctx::MAX_SETS; q++) xfree(c, c->d_recvs[q][d]);
+      xfree(c, c->d_push[d]);
    }
    for (size_t r = 0; r < c->peer_win.size(); r++)
       if (c->peer_ipc[r]) cudaIpcCloseMemHandle(c->peer_win[r]);
-   cudaFree(c->win);
-   cudaFree(c->d_peer_win);
-   cudaFree(c->d_credit);
-   cudaFree(c->d_push_done);
-   cudaFree(c->d_mv_moves);
-   cudaFree(c->d_mv_k);
-   cudaFree(c->d_mv_ranks);
-   cudaFree(c->d_cur);
+   xfree(c, c->win);
+   xfree(c, c->d_peer_win);
+   xfree(c, c->d_credit);
+   xfree(c, c->d_push_done);
+   xfree(c, c->d_mv_moves);
+   xfree(c, c->d_mv_k);
+   xfree(c, c->d_mv_ranks);
+   xfree(c, c->d_cur);
    if (c->h_p2p_err) cudaFreeHost(c->h_p2p_err);
    for (void *g : c->garbage) cudaFree(g);
+   cudaFree(c->arena);
 
-   cudaFree(c->d_partials);
-   cudaFree(c->d_cspart);
-   cudaFree(c->d_sums);
+   xfree(c, c->d_partials);
+   xfree(c, c->d_cspart);
+   xfree(c, c->d_sums);
    if (c->h_sums) cudaFreeHost(c->h_sums);
-   cudaFree(c->d_rops);
-   cudaFree(c->d_payload);
-   cudaFree(c->d_s0_a0);
-   cudaFree(c->d_s0_work);
-   cudaFree(c->d_s0_chk);
+   xfree(c, c->d_rops);
+   xfree(c, c->d_payload);
+   xfree(c, c->d_s0_a0);
+   xfree(c, c->d_s0_work);
+   xfree(c, c->d_s0_chk);
    if (c->h_s0_chk) cudaFreeHost(c->h_s0_chk);
-   cudaFree(c->d_mv_send);
-   cudaFree(c->d_mv_recv);
+   xfree(c, c->d_mv_send);
+   xfree(c, c->d_mv_recv);
    if (c->h_stage) cudaFreeHost(c->h_stage);
-   for (int o = 0; o < 6; o++) cudaFree(c->d_order_ord[o]);
+   for (int o = 0; o < 6; o++) xfree(c, c->d_order_ord[o]);
    if (c->ev_data) cudaEventDestroy(c->ev_data);
    if (c->ev_xchg) cudaEventDestroy(c->ev_xchg);
    for (int b = 0; b < 2; b++) {
-      cudaFree(c->d_up[b]);
+      xfree(c, c->d_up[b]);
       if (c->ev_up_copy[b]) cudaEventDestroy(c->ev_up_copy[b]);
       if (c->ev_up_fill[b]) cudaEventDestroy(c->ev_up_fill[b]);
    }
@@ -1805,6 +1831,7 @@ void mamr_destroy(mamr_ctx *c)
    if (c->ev_begin) cudaEventDestroy(c->ev_begin);
    if (c->ev_end) cudaEventDestroy(c->ev_end);
    if (c->stream) cudaStreamDestroy(c->stream);
+   cudaGetLastError();
    delete c;
 }
 
@@ -2738,12 +2765,11 @@ int mamr_p2p_connect(mamr_ctx *c, const char *handles)
             cudaGetLastError();
          }
          c->peer_win[r] = (char *)(uintptr_t)b.ptr;
-         if (!c->p2p_inproc) {
-            // stream-ordered allocations (dalloc) never hand memory back to the driver
-            cudaMemPool_t pool;
-            unsigned long long keep = ~0ULL;
-            CU(cudaDeviceGetDefaultMemPool(&pool, dev));
-            CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+         if (!c->arena) {
+            size_t mb = 128;
+            if (const char *e = getenv("MAMR_INPROC_ARENA_MB")) mb = (size_t)std::max(1, atoi(e));
+            c->arena_cap = mb << 20;
+            CU(cudaMalloc(&c->arena, c->arena_cap));
          }
          c->p2p_inproc = true;
       } else {

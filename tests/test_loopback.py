@@ -1,5 +1,6 @@
-"""The off-rank path on ONE GPU (runs under the driver's single-GPU `pytest -m gpu`): N ranks as
-N contexts in this process, connected through the peer-memory transport (tests/loopback.py).
+"""The off-rank path on ONE GPU (runs under the driver's single-GPU `pytest -m gpu`): N ranks that
+share the GPU -- threads of one fresh process per case, and for a few cases one process per rank
+(CUDA IPC) -- connected through the peer-memory transport (tests/loopback.py).
 Same cases and same oracle comparison as tests/test_multi_gpu.py (which needs N GPUs): pack
 kernels (boxop_kernel) reading resolved origins and earlier receive buffers, widened Y/Z faces
 forwarded through up to three ranks, receive-buffer reads inside fused2 / slab7, staged comm
@@ -8,25 +9,26 @@ import os
 
 import pytest
 
-from loopback import run_uniform_case
+from loopback import run_ranks
 from test_multi_gpu import CASES
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("fused", [1, 0])
+def world_of(cfg):
+    return cfg["np"][0]*cfg["np"][1]*cfg["np"][2]
+
+
 @pytest.mark.parametrize("case", range(len(CASES)))
-def test_ranks_on_one_gpu_match_single_rank_oracle(case, fused):
-    old = os.environ.get("MAMR_NO_FUSED")
-    os.environ["MAMR_NO_FUSED"] = "0" if fused else "1"
-    try:
-        out = run_uniform_case(CASES[case])
-    finally:
-        if old is None:
-            os.environ.pop("MAMR_NO_FUSED", None)
-        else:
-            os.environ["MAMR_NO_FUSED"] = old
-    assert len(out) == CASES[case]["np"][0]*CASES[case]["np"][1]*CASES[case]["np"][2]
+def test_ranks_on_one_gpu_match_single_rank_oracle(case):
+    run_ranks("uniform", world_of(CASES[case]), CASES[case])
+
+
+@pytest.mark.parametrize("case", [0, 1, 3, 5, 9, 12, 15])
+def test_split_path_ranks_on_one_gpu(case):
+    """MAMR_NO_FUSED=1: ghost cells materialised by the split path (pack / unpack kernels of
+    ghost.cu around the same transport)"""
+    run_ranks("uniform", world_of(CASES[case]), CASES[case], env={"MAMR_NO_FUSED": "1"})
 
 
 BASELINE_SHAPES = [
@@ -41,7 +43,7 @@ BASELINE_SHAPES = [
 
 @pytest.mark.parametrize("case", range(len(BASELINE_SHAPES)))
 def test_baseline_variable_counts_on_eight_ranks(case):
-    run_uniform_case(BASELINE_SHAPES[case])
+    run_ranks("uniform", world_of(BASELINE_SHAPES[case]), BASELINE_SHAPES[case])
 
 
 def test_block_migration_between_ranks_on_one_gpu():
@@ -49,76 +51,16 @@ def test_block_migration_between_ranks_on_one_gpu():
     (pull): 4 ranks, every rank sends two blocks to the next rank and one to the one after it.
     Half of the variables live in the second pool when the blocks move (rcb.c:207-337 payloads,
     pack.c:66-70 layout); the moved blocks then take part in one more stage."""
-    import numpy as np
-    from loopback import Ranks, connect
-    from miniamr_b200.capi import DeviceMesh
-    from oracle.oracle import OracleMesh
+    run_ranks("migration", 4, dict(n=[4, 6, 8], vars=5))
 
-    world, (nx, ny, nz), V, MB = 4, (4, 6, 8), 5, 12
-    shape = (V, nx + 2, ny + 2, nz + 2)
 
-    def seed(rank, slot):
-        return np.random.RandomState(1000*rank + slot + 7).random_sample(shape)
+@pytest.mark.parametrize("case", [0, 4, 7, 8])
+def test_two_processes_share_one_gpu(case):
+    """one PROCESS per rank: windows mapped with CUDA IPC (between processes on one device just as
+    between devices); the ranks' kernels are time-sliced, which is why only 2-rank cases run so"""
+    assert world_of(CASES[case]) == 2
+    run_ranks("uniform", 2, CASES[case], processes=True)
 
-    def isolated(slots):
-        n = len(slots)
-        return (np.asarray(slots, np.int32), np.zeros(n, np.int32), np.full((n, 6), -2, np.int32),
-                np.zeros((n, 6, 2, 2), np.int32))
 
-    # the oracle, rank by rank: stage 0 on slots 0..5 (variables 0..2 only), the moves, stage 1
-    orc = []
-    for r in range(world):
-        m = OracleMesh(nx, ny, nz, V, MB)
-        m.set_topology(*isolated(range(6)))
-        for s in range(6):                # slots that were never active hold zeros (both pools)
-            m.data[s] = seed(r, s)
-        m.comm(0, 3, 0)
-        for v in range(3):
-            m.stencil_driver(v, 0)
-        orc.append(m)
-    before = [{s: m.data[s].copy() for s in range(MB)} for m in orc]
-    for r in range(world):
-        m = orc[r]
-        for dst, (src_rank, src_slot) in {6: ((r - 1) % world, 0), 7: ((r - 1) % world, 2),
-                                          8: ((r - 2) % world, 4)}.items():
-            m.data[dst][:, 1:-1, 1:-1, 1:-1] = before[src_rank][src_slot][:, 1:-1, 1:-1, 1:-1]
-        m.set_topology(*isolated([1, 3, 5, 6, 7, 8]))
-        m.stage(1)
-
-    def rank_main(rank, ctx):
-        d = DeviceMesh(nx, ny, nz, V, MB, device=0, rank=rank, num_ranks=world)
-        try:
-            d.set_topology(*isolated(range(6)))
-            connect(d, rank, ctx)
-            for s in range(6):
-                d.upload_block(s, seed(rank, s))
-            d.comm(0, 3, 0)
-            for v in range(3):
-                d.stencil_driver(v, 0)                # variables 0..2 now live in the other pool
-            nxt, nx2, prv, pr2 = (rank + 1) % world, (rank + 2) % world, (rank - 1) % world, (rank - 2) % world
-            d.stage_send_block(0, nxt)
-            d.stage_recv_block(6, prv)
-            d.stage_send_block(2, nxt)
-            d.stage_send_block(4, nx2)
-            d.stage_recv_block(7, prv)
-            d.stage_recv_block(8, pr2)
-            assert d.pending_block_moves() == 6
-            d.flush_block_moves()
-            assert d.pending_block_moves() == 0
-            d.sync()                                  # reports a wait that timed out
-            d.set_topology(*isolated([1, 3, 5, 6, 7, 8]))
-            d.stage(1)
-            for s in (1, 3, 5, 6, 7, 8):
-                bad = d.download_block(s).view(np.uint64) != orc[rank].data[s].view(np.uint64)
-                assert not bad.any(), f"rank {rank} slot {s}: {int(bad.sum())} cells differ, first {np.argwhere(bad)[0]}"
-            assert d.counters()["migrate_bytes"] == 3*V*nx*ny*nz*8
-            d.flush_block_moves()                     # a round without moves on any rank
-            ctx.barrier()
-        finally:
-            try:
-                ctx.barrier()
-            except Exception:
-                pass
-            d.close()
-
-    Ranks(world).run(rank_main)
+def test_block_migration_between_two_processes():
+    run_ranks("migration", 3, dict(n=[4, 4, 4], vars=4), processes=True)

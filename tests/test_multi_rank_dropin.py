@@ -100,7 +100,10 @@ def test_n_rank_run_matches_reference(name):
     if ngpus() < 1:
         pytest.skip("needs a GPU")
     # fewer GPUs than ranks: the ranks share GPUs (rank r -> GPU r mod count); the peer-memory
-    # transport maps windows between processes on one device just as between devices
+    # transport maps windows between processes on one device just as between devices.  Their
+    # kernels are then time-sliced: 8 ranks on one GPU take minutes, so those wait for >= 2 GPUs.
+    if n >= 8 and ngpus() < 2:
+        pytest.skip("8 ranks on one GPU: time-sliced, too slow for the default suite")
     ref = run_ranks("ref_mp", n, args.split())
     dev = run_ranks("int_mp", n, args.split())
     compare(name, ref, dev, args)

@@ -374,10 +374,10 @@ def run_ours(args):
         d.check_sum_vars(0, V)
     barrier()
     d.timer_begin()
-    for st in range(args.steps):
+    for st in range(args.steps if not args.quick else 2):
         d.stage(args.warmup + args.steps + 2 + st)
         d.check_sum_vars(0, V)
-    ms_cs = d.timer_end()
+    ms_cs = d.timer_end()*(1.0 if not args.quick else args.steps/2.0)
     barrier()
     if world > 1:
         t = torch.tensor([ms_cs], dtype=torch.float64, device="cuda")
@@ -421,12 +421,17 @@ def run_ours(args):
             ms_ = float(t_.item())
         return ms_
 
-    e2e_job(1, False)                                  # warm the path
-    e2e_ms = e2e_job(args.steps, False)
-    e2e_val = upd_per_step*args.steps/(e2e_ms*1e-3)
-    strict_steps = max(1, min(args.steps, 3))
-    strict_ms = e2e_job(strict_steps, True)
-    strict_val = upd_per_step*strict_steps/(strict_ms*1e-3)
+    if args.quick:      # device-resident numbers only (multi-GPU A/B runs: box time is N times as dear)
+        e2e_ms = strict_ms = 0.0
+        e2e_val = strict_val = None
+        strict_steps = 0
+    else:
+        e2e_job(1, False)                                  # warm the path
+        e2e_ms = e2e_job(args.steps, False)
+        e2e_val = upd_per_step*args.steps/(e2e_ms*1e-3)
+        strict_steps = max(1, min(args.steps, 3))
+        strict_ms = e2e_job(strict_steps, True)
+        strict_val = upd_per_step*strict_steps/(strict_ms*1e-3)
 
     line = None
     if rank == 0:
@@ -476,7 +481,7 @@ def run_ours(args):
                     "ms_total": e2e_ms,
                     "reupload_every_step": {"value": strict_val, "steps": strict_steps,
                                             "h2d_bytes_per_step": h2d_bytes,
-                                            "ms_per_step": strict_ms/strict_steps}},
+                                            "ms_per_step": strict_ms/max(1, strict_steps)}},
             "with_checksum_every_stage": {"value": upd_per_step*args.steps/(ms_cs*1e-3), "unit": UNIT,
                                           "ms_per_step": ms_cs/args.steps,
                                           "what": "stage + check_sum of all variables (partials produced by "
@@ -494,7 +499,7 @@ def run_ours(args):
     # weak-scaling 32^3 7-point mesh) at every N, the refined configs[0] mesh (cfg1) at N=1.
     also = {}
     if args.workload == "cfg2" and not args.no_also:
-        for wn in (["cfg3"] + (["cfg1"] if world == 1 else [])):
+        for wn in (["cfg3"] + (["cfg1"] if world == 1 and not args.quick else [])):
             try:
                 A = resident_leg(wn, 0, args.steps, host=host)
                 host = A["host"]
@@ -526,6 +531,8 @@ def run_ours(args):
             except Exception as e:   # the baseline never gates the bench line
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0,
                                         "kind": "reference", "sample": f"failed: {e}"}
+        if args.quick:
+            line["e2e"] = None
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -544,6 +551,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--transport", default=os.environ.get("MAMR_TRANSPORT", "p2p"), choices=["p2p", "nccl"],
                     help="N > 1: ghost exchange by stores into peer memory (default) or NCCL send/recv")
+    ap.add_argument("--quick", action="store_true", help="device-resident legs only (no e2e)")
     ap.add_argument("--no-also", action="store_true", help="skip the cfg3 / cfg1 device-resident legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -245,6 +245,26 @@ int mamr_kernel_time_ms(mamr_ctx *ctx, float *stencil_ms, float *ghost_ms,
                         float *checksum_ms, long long *stencil_launches,
                         long long *ghost_launches, long long *checksum_launches);
 
+/* Device time by kernel kind, accumulated while kernel timing is enabled
+ * (mamr_kernel_timing): what the reference books with timer() around comm(),
+ * stencil_driver() and check_sum() (driver.c:80-106; comm.c:128-230 for the parts of
+ * comm) cannot be measured on the host when the device runs asynchronously.  wait == 0
+ * returns what has finished so far without synchronising. */
+typedef struct {
+   double fused_ms;        /* comm + stencil_calc in one kernel (fused stage kernels)        */
+   double stencil_ms;      /* stencil_calc / --stencil 0 kernels on materialised ghosts     */
+   double split_ghost_ms;  /* on_proc_comm, on_proc_comm_diff, apply_bc, pack_face kernels
+                              of the split path (comm.c:162-203)                            */
+   double pack_ms;         /* pack_face from resolved origins (comm.c:254-401)               */
+   double exchange_ms;     /* message transfer + waiting for the partners (comm.c:120-157)   */
+   double unpack_ms;       /* unpack_face (comm.c:1002-1150)                                 */
+   double regen_ms;        /* ghost layers / Z-face exports made real on demand              */
+   double checksum_ms;     /* check_sum kernels (check_sum.c:43-56)                          */
+   double allreduce_ms;    /* check_sum.c:57                                                 */
+   double halo_fraction;   /* part of fused_ms that is the exchange: halo bytes / all bytes  */
+} mamr_device_times;
+int mamr_get_device_times(mamr_ctx *ctx, int wait, mamr_device_times *out);
+
 #ifdef __cplusplus
 }
 #endif

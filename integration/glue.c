@@ -111,6 +111,9 @@ static void ensure_ctx(void)
    }
    stage_tile = (double *) malloc((size_t)num_vars*tile_doubles()*sizeof(double));
    memset(&seen, 0, sizeof seen);
+   memset(&seen_t, 0, sizeof seen_t);
+   dev_timers = !(getenv("MAMR_DEVICE_TIMERS") && !atoi(getenv("MAMR_DEVICE_TIMERS")));
+   if (dev_timers) OK(mamr_kernel_timing(G, 1), "kernel_timing");
    /* --stencil 0: the coefficients init() drew from rand() (init.c:418-423) */
    if (!stencil) OK(mamr_set_stencil0(G, mat, a1, a0), "set_stencil0");
 }
@@ -149,6 +152,7 @@ static void upload_host_blocks(void)
 }
 
 static void pull_counters(void);
+static double attribute_times(int wait);
 
 /* everything queued has run and every counter has reached the reference's globals */
 static void settle_counters(void)
@@ -156,6 +160,7 @@ static void settle_counters(void)
    if (!G) return;
    OK(mamr_sync(G), "sync");      /* also folds the per-cell flop counts of stencil_check */
    pull_counters();
+   attribute_times(1);
 }
 
 /* device -> blocks[].array for every active block (plot, debugging, tests) */
@@ -250,6 +255,58 @@ static void pull_counters(void)
    seen = c;
 }
 
+/* ---- timers ------------------------------------------------------------------
+ * driver.c:80-106 books host wall time around comm(), stencil_driver() and check_sum().
+ * The device runs asynchronously, so all of a stage's time would land wherever the host
+ * happens to block (check_sum's read-back).  Instead the library times its kernels with CUDA
+ * events by kind and this file adds that to the reference's timers whenever it looks (no
+ * extra synchronisation): fused comm+stencil kernels are split by their byte shares, the
+ * comm part over directions and face kinds by the face counts of comm.c:169-196.  What the
+ * host waited inside check_sum() for kernels of the other kinds is taken out of
+ * timer_cs_all again.  MAMR_DEVICE_TIMERS=0: host wall time only, as before. */
+static mamr_device_times seen_t;
+static int dev_timers = -1;
+
+static double attribute_times(int wait)
+{
+   mamr_device_times t;
+   mamr_counters c;
+   double calc, cfused, local, pack, xchg, unpack, faces[3], tot = 0.0, w;
+   int d;
+   if (!G || dev_timers <= 0) return 0.0;
+   OK(mamr_get_device_times(G, wait, &t), "get_device_times");
+   OK(mamr_get_counters(G, &c), "get_counters");
+   calc = 1e-3*((t.fused_ms - seen_t.fused_ms)*(1.0 - t.halo_fraction) + (t.stencil_ms - seen_t.stencil_ms));
+   cfused = 1e-3*(t.fused_ms - seen_t.fused_ms)*t.halo_fraction;
+   local = cfused + 1e-3*((t.split_ghost_ms - seen_t.split_ghost_ms) + (t.regen_ms - seen_t.regen_ms));
+   pack = 1e-3*(t.pack_ms - seen_t.pack_ms);
+   xchg = 1e-3*(t.exchange_ms - seen_t.exchange_ms);
+   unpack = 1e-3*(t.unpack_ms - seen_t.unpack_ms);
+   timer_calc_all += calc;
+   timer_comm_all += local + pack + xchg + unpack;
+   for (d = 0; d < 3; d++) {
+      faces[d] = (double)(c.counter_same[d] + c.counter_diff[d] + c.counter_bc[d] + c.counter_face_send[d]);
+      tot += faces[d];
+   }
+   for (d = 0; d < 3; d++) {
+      double on = (double)(c.counter_same[d] + c.counter_diff[d] + c.counter_bc[d]);
+      w = tot > 0.0 ? faces[d]/tot : 1.0/3.0;
+      timer_comm_dir[d] += (local + pack + xchg + unpack)*w;
+      if (on > 0.0) {
+         timer_comm_same[d] += local*w*(double)c.counter_same[d]/on;
+         timer_comm_diff[d] += local*w*(double)c.counter_diff[d]/on;
+         timer_comm_bc[d] += local*w*(double)c.counter_bc[d]/on;
+      }
+      timer_comm_pack[d] += pack*w;
+      timer_comm_wait[d] += xchg*w;          /* transfer + waiting for the partner */
+      timer_comm_unpack[d] += unpack*w;
+   }
+   timer_cs_calc += 1e-3*(t.checksum_ms - seen_t.checksum_ms);
+   timer_cs_red += 1e-3*(t.allreduce_ms - seen_t.allreduce_ms);
+   seen_t = t;
+   return calc + local + pack + xchg + unpack;
+}
+
 static int sync_timers(void)
 {
    static int v = -1;
@@ -267,10 +324,14 @@ void comm(int start, int num_comm, int stage)
    OK(mamr_comm(G, start, num_comm, stage), "comm");
    pull_counters();
    if (sync_timers()) OK(mamr_sync(G), "sync");
-   /* the three phases run as one device pass: the reference's per-direction
-      timers get an equal share */
-   t1 = (timer() - t1)/3.0;
-   for (d = 0; d < 3; d++) timer_comm_dir[d] += t1;
+   if (dev_timers > 0)
+      attribute_times(0);                 /* what has finished so far, by kind */
+   else {
+      /* the three phases run as one device pass: the reference's per-direction
+         timers get an equal share */
+      t1 = (timer() - t1)/3.0;
+      for (d = 0; d < 3; d++) timer_comm_dir[d] += t1;
+   }
 }
 
 void stencil_driver(int var, int calc_stage)
@@ -290,7 +351,13 @@ double check_sum(int var)
    ready();
    OK(mamr_check_sum(G, var, &sum), "check_sum");
    pull_counters();
-   timer_cs_calc += timer() - t1;     /* reduction included: one device pass */
+   if (dev_timers > 0) {
+      /* the caller books this call's wall time as check-sum time (driver.c:105); the part of
+         it spent waiting for comm / stencil kernels goes where it belongs */
+      double other = attribute_times(0), wall = timer() - t1;
+      timer_cs_all -= other < wall ? other : wall;
+   } else
+      timer_cs_calc += timer() - t1;     /* reduction included: one device pass */
    total_red++;
    return sum;
 }

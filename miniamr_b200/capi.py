@@ -67,7 +67,7 @@ EXPORTS = [
     "mamr_pending_block_moves", "mamr_device_count",
     "mamr_nccl_get_unique_id", "mamr_nccl_init", "mamr_p2p_get_handle", "mamr_p2p_connect",
     "mamr_timer_begin",
-    "mamr_timer_end", "mamr_kernel_timing", "mamr_kernel_time_ms",
+    "mamr_timer_end", "mamr_kernel_timing", "mamr_kernel_time_ms", "mamr_get_device_times",
     "mamr_plan_create", "mamr_plan_phase_dir", "mamr_plan_num_ops", "mamr_plan_get_ops",
     "mamr_plan_block_begin", "mamr_plan_destroy",
 ]
@@ -407,6 +407,15 @@ class DeviceMesh:
 
     def kernel_timing(self, enable=True):
         self._ck(self.L.mamr_kernel_timing(self.h, 1 if enable else 0))
+
+    def device_times(self, wait=True):
+        class T(C.Structure):
+            _fields_ = [(n, C.c_double) for n in
+                        ("fused_ms", "stencil_ms", "split_ghost_ms", "pack_ms", "exchange_ms", "unpack_ms",
+                         "regen_ms", "checksum_ms", "allreduce_ms", "halo_fraction")]
+        t = T()
+        self._ck(self.L.mamr_get_device_times(self.h, 1 if wait else 0, C.byref(t)))
+        return {n: getattr(t, n) for n, _ in T._fields_}
 
     def kernel_times(self):
         s, g, c = C.c_float(), C.c_float(), C.c_float()

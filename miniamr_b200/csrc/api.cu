@@ -100,7 +100,7 @@ bool load_nccl()
       if (r_ != MAMR_OK) return r_;  \
    } while (0)
 
-struct EventPair { cudaEvent_t a, b; int cls; };
+struct EventPair { cudaEvent_t a, b; int cls, detail; };
 
 struct mamr_ctx {
    mamr_params p;
@@ -147,8 +147,10 @@ struct mamr_ctx {
    int *d_lbegin[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
    bool plan_has_ident[6] = {false, false, false, false, false, false};
    HaloPlan plan[6];
-   std::vector<BoxOp> pack[6][3];       // multi-GPU: send-buffer fill per phase
+   std::vector<BoxOp> pack[6][3];       // multi-GPU: send-buffer fill per phase, CSR by face
+   std::vector<int> pack_fb[6][3];
    BoxOp *d_pack[6][3] = {};
+   int *d_pack_fb[6][3] = {};
    bool plan_built[6] = {false, false, false, false, false, false};
    BoxOp *d_hops[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
    int *d_hbegin[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -296,11 +298,13 @@ struct mamr_ctx {
    std::vector<cudaEvent_t> ev_free;
    double k_ms[3] = {0, 0, 0};
    long long k_launches[3] = {0, 0, 0};
+   double kd_ms[16] = {};      // the same by kernel kind (KD_*): mamr_get_device_times
 };
 
 namespace {
 
 enum { KC_STENCIL = 0, KC_GHOST = 1, KC_CHECKSUM = 2 };
+enum { KD_FUSED = 0, KD_STENCIL, KD_SPLIT, KD_PACK, KD_XCHG, KD_UNPACK, KD_REGEN, KD_CS, KD_ALLRED, KD_NUM };
 
 int dfree(mamr_ctx *c, void *p);
 template <typename T> int dalloc(mamr_ctx *c, T **p, size_t bytes);
@@ -340,8 +344,10 @@ struct KTimer {
    EventPair ep;
    bool on;
    cudaStream_t st;
-   KTimer(mamr_ctx *c_, int cls, cudaStream_t st_ = nullptr) : c(c_), on(c_->ktiming), st(st_ ? st_ : c_->stream)
+   KTimer(mamr_ctx *c_, int cls, cudaStream_t st_ = nullptr, int detail = -1)
+      : c(c_), on(c_->ktiming), st(st_ ? st_ : c_->stream)
    {
+      ep.detail = detail;
       if (!on) return;
       for (cudaEvent_t *e : { &ep.a, &ep.b }) {
          if (!c->ev_free.empty()) {
@@ -361,18 +367,26 @@ struct KTimer {
    }
 };
 
-void drain_ktimers(mamr_ctx *c)
+// fold the timed intervals into the totals; wait == false: only those that have finished
+void drain_ktimers(mamr_ctx *c, bool wait = true)
 {
+   size_t keep = 0;
    for (EventPair &ep : c->kev) {
+      if (!wait && cudaEventQuery(ep.b) != cudaSuccess) {
+         c->kev[keep++] = ep;
+         continue;
+      }
       float ms = 0.f;
       cudaEventSynchronize(ep.b);
       cudaEventElapsedTime(&ms, ep.a, ep.b);
       c->k_ms[ep.cls] += ms;
       c->k_launches[ep.cls]++;
+      if (ep.detail >= 0) c->kd_ms[ep.detail] += ms;
       c->ev_free.push_back(ep.a);
       c->ev_free.push_back(ep.b);
    }
-   c->kev.clear();
+   c->kev.resize(keep);
+   cudaGetLastError();      // cudaErrorNotReady of a query is not an error
 }
 
 // in-face axes in buffer order (slow, fast): comm.c:266-270, 311-320, 361-370
@@ -884,19 +898,19 @@ int comm_split(mamr_ctx *c, int start, int num, int ord, int buf_var0, bool exch
       const DirLists &L = c->cl[d];
       if (!c->ops_main[d].empty())
          for (const Run &r : runs) {
-            KTimer t(c, KC_GHOST);
+            KTimer t(c, KC_GHOST, nullptr, KD_SPLIT);
             launch_ghost(c->d_ops + c->off_main[d], (int)c->ops_main[d].size(), vpool(c, r.start), c->d_send[d],
                          c->d_recvs[set][d], c->g.var_stride, r.start, r.num, buf_var0, c->stream);
             c->cnt.kernel_launches++;
          }
       if (!L.partner.empty()) {
          if (exchange) {
-            KTimer t(c, KC_GHOST);
+            KTimer t(c, KC_GHOST, nullptr, KD_XCHG);
             CK(exchange_dir(c, d, c->stream, set));
          }
          if (!c->ops_unpack[d].empty())
             for (const Run &r : runs) {
-               KTimer t(c, KC_GHOST);
+               KTimer t(c, KC_GHOST, nullptr, KD_UNPACK);
                launch_ghost(c->d_ops + c->off_unpack[d], (int)c->ops_unpack[d].size(), vpool(c, r.start),
                             c->d_send[d], c->d_recvs[set][d], c->g.var_stride, r.start, r.num, buf_var0,
                             c->stream);
@@ -1042,7 +1056,7 @@ int ensure_plan(mamr_ctx *c, int ord)
       P.why = "more than 64 halo ops on one block";
    }
    for (int o = 0; o < 3 && P.ok && c->have_partners; o++)
-      if (!build_pack_plan(in, o, c->pack[ord][o], P.why)) P.ok = false;
+      if (!build_pack_plan(in, o, c->pack[ord][o], c->pack_fb[ord][o], P.why)) P.ok = false;
    c->plan_built[ord] = true;
    if (!P.ok) return MAMR_OK;
    CU(cudaStreamSynchronize(c->stream));
@@ -1136,12 +1150,18 @@ int ensure_plan(mamr_ctx *c, int ord)
    }
    for (int o = 0; o < 3; o++) {
       CK(dfree(c, c->d_pack[ord][o]));
+      CK(dfree(c, c->d_pack_fb[ord][o]));
       c->d_pack[ord][o] = nullptr;
+      c->d_pack_fb[ord][o] = nullptr;
       const std::vector<BoxOp> &K = c->pack[ord][o];
+      const std::vector<int> &FB = c->pack_fb[ord][o];
       if (!c->have_partners || K.empty()) continue;
       CK(dalloc(c, &c->d_pack[ord][o], K.size()*sizeof(BoxOp)));
       CU(cudaMemcpyAsync(c->d_pack[ord][o], K.data(), K.size()*sizeof(BoxOp),
                          cudaMemcpyHostToDevice, c->stream));
+      CK(dalloc(c, &c->d_pack_fb[ord][o], FB.size()*sizeof(int)));
+      CU(cudaMemcpyAsync(c->d_pack_fb[ord][o], FB.data(), FB.size()*sizeof(int), cudaMemcpyHostToDevice,
+                         c->stream));
    }
    CU(cudaStreamSynchronize(c->stream));
    return MAMR_OK;
@@ -1175,7 +1195,7 @@ int regen_ghosts(mamr_ctx *c, int v0, int n)
       if (!c->plan_built[ord] || !c->plan[ord].ok || !c->d_hops[ord])
          return fail(MAMR_EINVAL, "internal: halo plan of an elided stage is gone");
       if (c->num_active > 0) {
-         KTimer t(c, KC_GHOST);
+         KTimer t(c, KC_GHOST, nullptr, KD_REGEN);
          double *const *rs = c->d_recvs[c->stale_set[v]];
          const double *recv[3] = { rs[0], rs[1], rs[2] };
          launch_halo_fill(c->d_hops[ord], c->d_hbegin[ord], c->d_slots, c->num_active, c->pool[in],
@@ -1228,7 +1248,7 @@ int run_stencil0(mamr_ctx *c, int pool, int v0, int n)
       const bool plain = v == 0 || v >= 4*mat;
       int e = v + 1;
       while (e < v0 + n && (e == 0 || e >= 4*mat) == plain) e++;
-      KTimer t(c, KC_STENCIL);
+      KTimer t(c, KC_STENCIL, nullptr, KD_STENCIL);
       if (plain)
          launch_stencil(c->pool[pool], c->g, c->d_slots, c->num_active, v, e - v, 7, c->stream);
       else
@@ -1296,7 +1316,7 @@ int flush_pending(mamr_ctx *c)
             for (int v = r.start; v < r.start + r.num; v++) synced = synced && c->shell_synced[v];
             if (!synced) {
                CK(wait_xchg(c));
-               KTimer t(c, KC_GHOST);
+               KTimer t(c, KC_GHOST, nullptr, KD_REGEN);
                launch_halo_fill(c->d_hops[ord], c->d_hbegin[ord], c->d_slots, c->num_active,
                                 c->pool[in], c->pool[in ^ 1], c->g, recv, r.start, r.num,
                                 c->pc_start[r.start], true, c->stream);
@@ -1310,7 +1330,7 @@ int flush_pending(mamr_ctx *c)
                if (c->zf_ok[v]) { v++; continue; }
                int e = v;
                while (e < r.start + r.num && !c->zf_ok[e]) e++;
-               KTimer t(c, KC_GHOST);
+               KTimer t(c, KC_GHOST, nullptr, KD_REGEN);
                launch_zface_extract(c->pool[in], c->zf[in], c->g, c->d_slots, c->num_active, v,
                                     e - v, c->stream);
                c->cnt.kernel_launches++;
@@ -1349,7 +1369,7 @@ int flush_pending(mamr_ctx *c)
             // that waits for the exchange only, so their CTAs fill the machine as the
             // interior launch drains instead of waiting for its tail (both launches
             // read the same pool and write disjoint tiles).  One timed interval.
-            KTimer t(c, KC_STENCIL);
+            KTimer t(c, KC_STENCIL, nullptr, KD_FUSED);
             CU(cudaEventRecord(c->ev_pre, c->stream));
             launch(c->d_order_ord[ord], c->n_interior[ord], c->stream);
             CU(cudaStreamWaitEvent(c->bstream, c->ev_pre, 0));
@@ -1362,7 +1382,7 @@ int flush_pending(mamr_ctx *c)
             c->xchg_pending = false;
          } else {
             CK(wait_xchg(c));
-            KTimer t(c, KC_STENCIL);
+            KTimer t(c, KC_STENCIL, nullptr, KD_FUSED);
             launch(c->d_order, c->num_active, c->stream);
          }
          if (c->num_active > 0)
@@ -1380,7 +1400,7 @@ int flush_pending(mamr_ctx *c)
          if (c->p.stencil == 0)
             CK(run_stencil0(c, in, r.start, r.num));
          else {
-            KTimer t(c, KC_STENCIL);
+            KTimer t(c, KC_STENCIL, nullptr, KD_STENCIL);
             launch_stencil(c->pool[in], c->g, c->d_slots, c->num_active, r.start, r.num,
                            c->p.stencil, c->stream);
             if (c->num_active > 0) c->cnt.kernel_launches++;
@@ -1777,7 +1797,10 @@ void mamr_destroy(mamr_ctx *c)
       xfree(c, c->d_fsrc[o]);
       xfree(c, c->d_cops[o]);
       xfree(c, c->d_cbegin[o]);
-      for (int q = 0; q < 3; q++) xfree(c, c->d_pack[o][q]);
+      for (int q = 0; q < 3; q++) {
+         xfree(c, c->d_pack[o][q]);
+         xfree(c, c->d_pack_fb[o][q]);
+      }
    }
    xfree(c, c->d_slots);
    xfree(c, c->d_order);
@@ -2200,14 +2223,13 @@ int mamr_comm(mamr_ctx *c, int start, int num_comm, int stage)
             const int d = kPerm[ord][o];
             if (c->cl[d].partner.empty()) continue;
             for (const Run &r : runs_of(c, start, num_comm, false)) {
-               KTimer t(c, KC_GHOST, xs);
-               launch_boxops(c->d_pack[ord][o], (int)c->pack[ord][o].size(), vpool(c, r.start),
-                             vpool(c, r.start), c->g.var_stride, send, recv, r.start, r.num, start,
-                             xs);
+               KTimer t(c, KC_GHOST, xs, KD_PACK);
+               launch_facepack(c->d_pack[ord][o], c->d_pack_fb[ord][o], (int)c->pack_fb[ord][o].size() - 1,
+                               vpool(c, r.start), c->g.var_stride, send, recv, r.start, r.num, start, xs);
                c->cnt.kernel_launches++;
             }
             {
-               KTimer t(c, KC_GHOST, xs);
+               KTimer t(c, KC_GHOST, xs, KD_XCHG);
                CK(exchange_dir(c, d, xs, set));
             }
          }
@@ -2318,7 +2340,7 @@ int mamr_check_sum_vars(mamr_ctx *c, int var_start, int num, double *sums)
       const bool fz = c->cs_fused[v] && c->num_active > 0;
       int e = v + 1;
       while (e < var_start + num && (c->cs_fused[e] && c->num_active > 0) == fz) e++;
-      KTimer t(c, KC_CHECKSUM);
+      KTimer t(c, KC_CHECKSUM, nullptr, KD_CS);
       if (fz) {
          launch_checksum_final(c->d_cspart + (size_t)v*c->num_active*CS_WARPS, c->num_active*CS_WARPS,
                                e - v, c->d_sums + (v - var_start), c->stream);
@@ -2339,7 +2361,7 @@ int mamr_check_sum_vars(mamr_ctx *c, int var_start, int num, double *sums)
       while (u < c->p.num_vars && c->spec[u] && (c->spec_flags[u] & 2) && !c->spec_cs_ok[u]) u++;
       extra = u - (var_start + num);
       if (extra > 0) {
-         KTimer t(c, KC_CHECKSUM);
+         KTimer t(c, KC_CHECKSUM, nullptr, KD_CS);
          launch_checksum_final(c->d_cspart + (size_t)(var_start + num)*c->num_active*CS_WARPS,
                                c->num_active*CS_WARPS, extra, c->d_sums + num, c->stream);
          c->cnt.kernel_launches++;
@@ -2348,7 +2370,7 @@ int mamr_check_sum_vars(mamr_ctx *c, int var_start, int num, double *sums)
    CU(cudaGetLastError());
    if (c->p.num_ranks > 1) {      // check_sum.c:57
       if (c->p2p) {
-         KTimer t(c, KC_CHECKSUM);
+         KTimer t(c, KC_CHECKSUM, nullptr, KD_ALLRED);
          launch_p2p_allreduce(c->d_sums, num, c->d_peer_win, c->win, c->p.rank, c->p.num_ranks,
                               c->p.num_vars, ++c->cs_seq, c->stream);
          c->cnt.kernel_launches++;
@@ -2857,7 +2879,8 @@ int mamr_plan_create(const mamr_params *params, int num_active, const mamr_block
    build_halo_plan(in, P->halo);
    std::string why = P->halo.why;
    bool ok = P->halo.ok;
-   for (int o = 0; o < 3 && ok && partners; o++) ok = build_pack_plan(in, o, P->pack[o], why);
+   std::vector<int> fb;
+   for (int o = 0; o < 3 && ok && partners; o++) ok = build_pack_plan(in, o, P->pack[o], fb, why);
    if (!ok) {
       delete P;
       return fail(why.find("misconnected") != std::string::npos ? MAMR_ETOPOLOGY : MAMR_EUNSUPPORTED,
@@ -2934,6 +2957,32 @@ int mamr_kernel_timing(mamr_ctx *c, int enable)
    drain_ktimers(c);
    c->ktiming = enable != 0;
    for (int i = 0; i < 3; i++) { c->k_ms[i] = 0; c->k_launches[i] = 0; }
+   return MAMR_OK;
+}
+
+int mamr_get_device_times(mamr_ctx *c, int wait, mamr_device_times *out)
+{
+   if (!c || !out) return fail(MAMR_EINVAL, "null argument");
+   if (wait) {
+      CK(flush_pending(c));
+      CU(cudaStreamSynchronize(c->stream));
+      if (c->xstream) CU(cudaStreamSynchronize(c->xstream));
+   }
+   drain_ktimers(c, wait != 0);
+   out->fused_ms = c->kd_ms[KD_FUSED];
+   out->stencil_ms = c->kd_ms[KD_STENCIL];
+   out->split_ghost_ms = c->kd_ms[KD_SPLIT];
+   out->pack_ms = c->kd_ms[KD_PACK];
+   out->exchange_ms = c->kd_ms[KD_XCHG];
+   out->unpack_ms = c->kd_ms[KD_UNPACK];
+   out->regen_ms = c->kd_ms[KD_REGEN];
+   out->checksum_ms = c->kd_ms[KD_CS];
+   out->allreduce_ms = c->kd_ms[KD_ALLRED];
+   // share of a fused launch that is the ghost exchange: halo bytes / all bytes
+   const double n3 = (double)c->p.nx*c->p.ny*c->p.nz;
+   const double H = c->p.stencil == 7 ? 2.0*(c->p.nx*c->p.ny + c->p.ny*c->p.nz + c->p.nx*c->p.nz)
+                                      : (double)(c->p.nx + 2)*(c->p.ny + 2)*(c->p.nz + 2) - n3;
+   out->halo_fraction = 8.0*H/n3/(16.0 + 8.0*H/n3);
    return MAMR_OK;
 }
 

@@ -110,7 +110,9 @@ struct HaloPlan {
 // resolve every ghost region of every active block (fused kernel input)
 void build_halo_plan(const PlanInput &in, HaloPlan &out);
 // ops that fill the send buffer of direction phase `phase` from resolved sources
-bool build_pack_plan(const PlanInput &in, int phase, std::vector<BoxOp> &ops, std::string &why);
+// (fbegin: CSR of the ops by face of the direction's comm list, faces + 1 entries)
+bool build_pack_plan(const PlanInput &in, int phase, std::vector<BoxOp> &ops, std::vector<int> &fbegin,
+                     std::string &why);
 
 // split / consolidate work item: parent slot + 8 child slots
 struct RefineOp {
@@ -179,10 +181,10 @@ void launch_halo_fill(const BoxOp *d_ops, const int *d_begin, const int *d_slots
                       const double *pool_in, double *pool_out, const Geometry &g,
                       const double *const recv[3], int var_start, int num_vars, int buf_var0,
                       bool only_ident, cudaStream_t s);
-// generic executor of BoxOps whose destination is a send buffer or the pool
-void launch_boxops(const BoxOp *d_ops, int n_ops, const double *pool_in, double *pool_out,
-                   long long var_stride, double *const send[3], const double *const recv[3],
-                   int var_start, int num_vars, int buf_var0, cudaStream_t s);
+// pack_face of one direction phase: the BoxOps of face f are ops[fbegin[f] .. fbegin[f+1])
+void launch_facepack(const BoxOp *d_ops, const int *d_fbegin, int n_faces, const double *pool_in,
+                     long long var_stride, double *const send[3], const double *const recv[3],
+                     int var_start, int num_vars, int buf_var0, cudaStream_t s);
 int stencil_smem_bytes(const Geometry &g);
 bool stencil_configure(const Geometry &g, std::string &err);
 

@@ -431,59 +431,68 @@ void launch_fused(const double *pool_in, double *pool_out, const Geometry &g, co
 }
 
 // ---------------------------------------------------------------------------
-// Generic BoxOp executor: grid = (ops, variables).  Used to pack the send
-// buffers of the multi-GPU path from resolved origins (pack_face, comm.c:254-401).
+// pack_face (comm.c:254-401) of one direction phase from resolved origins: grid = (faces,
+// groups of PACK_VPC variables).  A face's message is filled by 1..9 BoxOps (its interior
+// run plus, for widened faces, the ghost rows / corners an earlier phase delivered --
+// possibly out of an earlier receive buffer); the CTA walks them for its variables, so a
+// one-cell corner op costs one loop trip instead of a CTA of its own.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-boxop_kernel(const BoxOp *__restrict__ ops, const double *__restrict__ pool_in,
-             double *__restrict__ pool_out, long long var_stride, double *send0, double *send1,
-             double *send2, const double *recv0, const double *recv1, const double *recv2,
-             int var_start, int buf_var0)
+constexpr int PACK_VPC = 8;
+
+__global__ void __launch_bounds__(256)
+facepack_kernel(const BoxOp *__restrict__ ops, const int *__restrict__ fbegin,
+                const double *__restrict__ pool_in, long long var_stride, double *send0, double *send1,
+                double *send2, const double *recv0, const double *recv1, const double *recv2,
+                int var_start, int var_end, int buf_var0)
 {
-   const BoxOp op = ops[blockIdx.x];
-   const int v = var_start + blockIdx.y;
+   const int v0 = var_start + blockIdx.y*PACK_VPC;
+   const int nv = min(PACK_VPC, var_end - v0);
    double *sends[3] = { send0, send1, send2 };
    const double *recvs[3] = { recv0, recv1, recv2 };
-   double *dst = (op.dst_mem == BM_POOL)
-                    ? pool_out + (long long)v*var_stride
-                    : sends[op.dst_mem - BM_BUF0] + (long long)(v - buf_var0)*op.dst_vs;
-   const double *src = (op.src_mem == BM_POOL)
-                          ? pool_in + (long long)v*var_stride
-                          : recvs[op.src_mem - BM_BUF0] + (long long)(v - buf_var0)*op.src_vs;
-   dst += op.dst_base;
-   src += op.src_base;
-   const int n = op.ext[0]*op.ext[1]*op.ext[2];
-   for (int e = threadIdx.x; e < n; e += blockDim.x) {
-      int r = e;
-      const int c = r%op.ext[2]; r /= op.ext[2];
-      const int b = r%op.ext[1];
-      const int a = r/op.ext[1];
-      double x;
-      if (op.mode == FM_COPY || op.mode == FM_DIV4) {
-         x = src[(long long)a*op.src_str[0] + b*op.src_str[1] + c*op.src_str[2]];
-         if (op.mode == FM_DIV4) x = x/4.0;
-      } else if (op.mode == FM_PROLONG || op.mode == FM_REPL) {
-         x = src[(long long)(a >> 1)*op.src_str[0] + (b >> 1)*op.src_str[1] + (c >> 1)*op.src_str[2]];
-         if (op.mode == FM_PROLONG) x = x/4.0;
-      } else {
-         const double *p = src + (long long)(2*a)*op.src_str[0] + (2*b)*op.src_str[1] +
-                           (2*c)*op.src_str[2];
-         x = p[0] + p[op.F];
-         x += p[op.S];
-         x += p[op.S + op.F];
+   for (int o = fbegin[blockIdx.x]; o < fbegin[blockIdx.x + 1]; o++) {
+      const BoxOp op = ops[o];
+      double *dst0 = sends[op.dst_mem - BM_BUF0] + op.dst_base;
+      const bool pool = op.src_mem == BM_POOL;
+      const double *src0 = (pool ? pool_in : recvs[op.src_mem - BM_BUF0]) + op.src_base;
+      const long long svs = pool ? var_stride : op.src_vs;
+      const int e1 = op.ext[1], e2 = op.ext[2];
+      const int n = op.ext[0]*e1*e2;
+      for (int w = threadIdx.x; w < n*nv; w += blockDim.x) {
+         const int t = w/n;
+         int r = w - t*n;
+         const int c = r%e2; r /= e2;
+         const int b = r%e1;
+         const int a = r/e1;
+         const int v = v0 + t;
+         const double *src = src0 + (pool ? (long long)v : (long long)(v - buf_var0))*svs;
+         double x;
+         if (op.mode == FM_COPY || op.mode == FM_DIV4) {
+            x = src[(long long)a*op.src_str[0] + b*op.src_str[1] + c*op.src_str[2]];
+            if (op.mode == FM_DIV4) x = x/4.0;
+         } else if (op.mode == FM_PROLONG || op.mode == FM_REPL) {
+            x = src[(long long)(a >> 1)*op.src_str[0] + (b >> 1)*op.src_str[1] + (c >> 1)*op.src_str[2]];
+            if (op.mode == FM_PROLONG) x = x/4.0;
+         } else {
+            const double *p = src + (long long)(2*a)*op.src_str[0] + (2*b)*op.src_str[1] +
+                              (2*c)*op.src_str[2];
+            x = p[0] + p[op.F];
+            x += p[op.S];
+            x += p[op.S + op.F];
+         }
+         dst0[(long long)(v - buf_var0)*op.dst_vs + (long long)a*op.dst_str[0] + b*op.dst_str[1] +
+              c*op.dst_str[2]] = x;
       }
-      dst[(long long)a*op.dst_str[0] + b*op.dst_str[1] + c*op.dst_str[2]] = x;
    }
 }
 
-void launch_boxops(const BoxOp *d_ops, int n_ops, const double *pool_in, double *pool_out,
-                   long long var_stride, double *const send[3], const double *const recv[3],
-                   int var_start, int num_vars, int buf_var0, cudaStream_t s)
+void launch_facepack(const BoxOp *d_ops, const int *d_fbegin, int n_faces, const double *pool_in,
+                     long long var_stride, double *const send[3], const double *const recv[3],
+                     int var_start, int num_vars, int buf_var0, cudaStream_t s)
 {
-   if (n_ops <= 0 || num_vars <= 0) return;
-   dim3 grid((unsigned)n_ops, (unsigned)num_vars);
-   boxop_kernel<<<grid, 128, 0, s>>>(d_ops, pool_in, pool_out, var_stride, send[0], send[1],
-                                     send[2], recv[0], recv[1], recv[2], var_start, buf_var0);
+   if (n_faces <= 0 || num_vars <= 0) return;
+   dim3 grid((unsigned)n_faces, (unsigned)((num_vars + PACK_VPC - 1)/PACK_VPC));
+   facepack_kernel<<<grid, 256, 0, s>>>(d_ops, d_fbegin, pool_in, var_stride, send[0], send[1], send[2],
+                                        recv[0], recv[1], recv[2], var_start, var_start + num_vars, buf_var0);
 }
 
 }  // namespace mamr

@@ -19,6 +19,8 @@
 //  * All strides are immediates; the halo gather of a block whose ops are plain
 //    pool copies (no level boundary, no receive buffer) is a table-driven loop of
 //    8-byte cp.async.
+#include <algorithm>
+
 #include "common.cuh"
 #include "ptx.cuh"
 #include "fused_common.cuh"
@@ -190,8 +192,10 @@ fused2_kernel(const FusedArgs A)
    // decode this thread's share of the halo once per block
    const int last = nops - 1;
    const int E = nops > 0 ? sops[last].first + sops[last].e0*sops[last].e1*sops[last].e2 : 0;
+   // dinfo: destination (20 bits) | op (6 bits) | mode (3 bits) | source memory (2 bits); a cell
+   // that is an 8-byte copy out of the pool -- all of them on a uniform single-rank mesh -- has
+   // nothing above bit 20 but its op index, which it never needs
    int soff[Q], dinfo[Q];
-   bool plain = true;     // every cell of this thread: 8-byte copy out of the pool
 #pragma unroll
    for (int q = 0; q < Q; q++) {
       const int e = tid + q*CT;
@@ -221,24 +225,18 @@ fused2_kernel(const FusedArgs A)
          else if (mode == FM_SUM4) o = (long long)(2*aa)*s.ss0 + (2*b)*s.ss1 + (2*c)*s.ss2;
          else o = (long long)(aa >> 1)*s.ss0 + (b >> 1)*s.ss1 + (c >> 1)*s.ss2;
          soff[q] = (int)(s.src_base + o);
-         dinfo[q] = dsto | (lo << 20) | (mode << 26) | (s.src_mem << 29);
-         if (mode != FM_COPY || s.src_mem != BM_POOL) plain = false;
+         const bool plain = mode == FM_COPY && s.src_mem == BM_POOL;
+         dinfo[q] = dsto | (plain ? 0 : ((lo << 20) | (mode << 26) | (s.src_mem << 29)));
       }
    }
-   const int nplain = __popc(__ballot_sync(0xffffffffu, plain));
-   __shared__ int s_notplain;
-   if (tid == 0) s_notplain = 0;
-   named_bar_sync(1, CT);
-   if (nplain != 32 && (tid & 31) == 0) atomicAdd(&s_notplain, 1);
-   named_bar_sync(1, CT);
-   const bool simple = s_notplain == 0;
 
-   // halo cell q of this thread for variable v -> buffer dst
+   // halo cell q of this thread for variable v -> buffer dst.  Per cell: the plain copy, or
+   // (level boundary, receive buffer) the op's transform -- only those cells pay for it
    auto gather_one = [&](int q, int v, double *dst) {
       if (dinfo[q] < 0) return;
       const double *pin = A.pool_in + (long long)v*A.var_stride;
-      if (simple) {
-         cp_async8(dst + (dinfo[q] & 0xfffff), pin + soff[q]);
+      if (!(dinfo[q] >> 20)) {
+         cp_async8(dst + dinfo[q], pin + soff[q]);
          return;
       }
       const int mode = (dinfo[q] >> 26) & 7, mem = dinfo[q] >> 29, op = (dinfo[q] >> 20) & 63;
@@ -533,7 +531,23 @@ void launch_fused2(const double *pool_in, double *pool_out, const Geometry &g, c
       vpc_env = e ? atoi(e) : 0;
    }
    A.chunk = 0;
-   A.vpc = vpc_env > 0 ? vpc_env : 20;
+   // Variables per CTA: 20 amortises the per-block work (op table, halo decode) best, but a small
+   // mesh must still give every SM several waves of CTAs or the last wave idles most of the GPU
+   // (785 blocks x 2 groups = 2.7 waves): aim at six waves, never fewer than 4 variables per CTA.
+   static int sms = 0;
+   if (!sms) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (sms <= 0) sms = 148;
+   }
+   int ctas_per_sm = 2;
+#define X(NN) if (g.n[0] == NN) ctas_per_sm = Shape<NN>::CTAS;
+   MAMR_FUSED2_SIZES(X)
+#undef X
+   const long long want = 6LL*sms*ctas_per_sm;
+   const int groups_wanted = (int)std::min<long long>(num_vars, (want + num_active - 1)/num_active);
+   A.vpc = vpc_env > 0 ? vpc_env : std::max(4, std::min(20, num_vars/std::max(1, groups_wanted)));
    if (A.vpc > num_vars) A.vpc = num_vars;
    A.var_start = var_start;
    A.var_end = var_start + num_vars;

@@ -397,7 +397,8 @@ void build_halo_plan(const PlanInput &in, HaloPlan &out)
 
 // pack_face code 0 (comm.c:254-401) for the faces of direction phase `phase`,
 // reading resolved origins instead of this rank's (unmaterialised) ghost cells
-bool build_pack_plan(const PlanInput &in, int phase, std::vector<BoxOp> &ops, std::string &why)
+bool build_pack_plan(const PlanInput &in, int phase, std::vector<BoxOp> &ops, std::vector<int> &fbegin,
+                     std::string &why)
 {
    Ctx c(in);
    const Geometry &g = c.g;
@@ -407,7 +408,9 @@ bool build_pack_plan(const PlanInput &in, int phase, std::vector<BoxOp> &ops, st
    face_axes(d, sa, fa);
    const long long S = g.str[sa], F = g.str[fa], N = g.str[d];
    ops.clear();
+   fbegin.assign(L.block.size() + 1, 0);
    for (size_t f = 0; f < L.block.size(); f++) {
+      fbegin[f] = (int)ops.size();
       const int slot = L.block[f];
       if (slot < 0 || slot >= in.max_blocks || c.slot2idx[slot] < 0) {
          why = "comm list names an inactive block";
@@ -475,6 +478,7 @@ bool build_pack_plan(const PlanInput &in, int phase, std::vector<BoxOp> &ops, st
          ops.push_back(op);
       }
    }
+   fbegin[L.block.size()] = (int)ops.size();
    return true;
 }
 

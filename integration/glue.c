@@ -46,6 +46,9 @@ static double *stage_tile;      /* one block, [var][i][j][k] contiguous         
 static int nccl_moves;          /* migrated block payloads travel GPU to GPU (peer
                                    memory or NCCL) instead of through send_buff      */
 
+static mamr_device_times seen_t; /* device times already added to the reference's timers  */
+static int dev_timers = -1;     /* MAMR_DEVICE_TIMERS (default 1)                         */
+
 static void die(const char *where)
 {
    printf("%d ERROR: miniamr_b200 %s: %s\n", my_pe, where, mamr_last_error());
@@ -264,9 +267,6 @@ static void pull_counters(void)
  * comm part over directions and face kinds by the face counts of comm.c:169-196.  What the
  * host waited inside check_sum() for kernels of the other kinds is taken out of
  * timer_cs_all again.  MAMR_DEVICE_TIMERS=0: host wall time only, as before. */
-static mamr_device_times seen_t;
-static int dev_timers = -1;
-
 static double attribute_times(int wait)
 {
    mamr_device_times t;

@@ -264,6 +264,7 @@ struct mamr_ctx {
    bool p2p = false;            // windows of all ranks are mapped: ghost messages and the
                                 // check_sum all-reduce go through them
    bool p2p_inproc = false;     // some peer lives in this process (loopback): see dfree()
+   double p2p_timeout_s = 20.0;
    char *win = nullptr;
    size_t win_bytes = 0, win_data_off = 0, win_data_cap = 0;   // capacity in doubles
    std::vector<char *> peer_win;          // mapped windows, by rank (mine included)
@@ -299,6 +300,16 @@ struct mamr_ctx {
    double k_ms[3] = {0, 0, 0};
    long long k_launches[3] = {0, 0, 0};
    double kd_ms[16] = {};      // the same by kernel kind (KD_*): mamr_get_device_times
+   // MAMR_TRACE=1: where a stage's time goes when an off-rank exchange overlaps the interior
+   // blocks' kernel.  Events: 0 comm() reached on the main stream, 1 exchange complete, 2 interior
+   // launch complete, 3 boundary launch starts, 4 boundary launch complete; means printed by
+   // mamr_destroy.
+   bool trace = false;
+   struct TraceRec { cudaEvent_t e[5]; int have; };
+   TraceRec tr_cur = {};
+   std::vector<TraceRec> tr_done;
+   double tr_sum[4] = {0, 0, 0, 0};
+   long long tr_n = 0;
 };
 
 namespace {
@@ -366,6 +377,38 @@ struct KTimer {
       c->kev.push_back(ep);
    }
 };
+
+void trace_mark(mamr_ctx *c, int i, cudaStream_t st)
+{
+   if (!c->trace) return;
+   if (i == 0) {
+      c->tr_cur.have = 0;
+      for (int k = 0; k < 5; k++) cudaEventCreate(&c->tr_cur.e[k]);
+   }
+   if (!c->tr_cur.e[i]) return;
+   cudaEventRecord(c->tr_cur.e[i], st);
+   c->tr_cur.have |= 1 << i;
+   if (i == 4) {
+      if (c->tr_cur.have == 31) c->tr_done.push_back(c->tr_cur);
+      c->tr_cur = {};
+   }
+}
+
+void trace_drain(mamr_ctx *c)
+{
+   for (mamr_ctx::TraceRec &r : c->tr_done) {
+      cudaEventSynchronize(r.e[4]);
+      cudaEventSynchronize(r.e[1]);
+      for (int k = 1; k < 5; k++) {
+         float ms = 0.f;
+         cudaEventElapsedTime(&ms, r.e[0], r.e[k]);
+         c->tr_sum[k - 1] += ms;
+      }
+      c->tr_n++;
+      for (int k = 0; k < 5; k++) cudaEventDestroy(r.e[k]);
+   }
+   c->tr_done.clear();
+}
 
 // fold the timed intervals into the totals; wait == false: only those that have finished
 void drain_ktimers(mamr_ctx *c, bool wait = true)
@@ -820,7 +863,7 @@ int p2p_check(mamr_ctx *c)
                          : (e >> 8) == 3 ? "ghost message" : (e >> 8) == 4 ? "check_sum contribution"
                          : (e >> 8) == 5 ? "migrated-block table" : "migration acknowledgement";
       return fail(MAMR_EP2P, "peer-memory transport: rank %d waited %.0f s for the %s of rank %d",
-                  c->p.rank, (double)P2P_TIMEOUT_NS*1e-9, what, (int)(e & 0xff));
+                  c->p.rank, c->p2p_timeout_s, what, (int)(e & 0xff));
    }
    return MAMR_OK;
 }
@@ -841,24 +884,45 @@ int p2p_begin(mamr_ctx *c, cudaStream_t st, int set)
 
 // one message per (direction, partner), comm.c:71-84 / 120-151: stores into the partners'
 // windows (p2p.cu), or NCCL send/recv
+void count_messages(mamr_ctx *c, int d)
+{
+   const DirLists &L = c->cl[d];
+   for (size_t i = 0; i < L.partner.size(); i++) {
+      c->cnt.counter_halo_recv[d]++;
+      c->cnt.counter_halo_send[d]++;
+      c->cnt.size_mesg_recv[d] += (double)L.recv_size[i]*sizeof(double);
+      c->cnt.size_mesg_send[d] += (double)L.send_size[i]*sizeof(double);
+      c->cnt.counter_face_send[d] += L.num[i];
+      c->cnt.counter_face_recv[d] += L.num[i];
+   }
+}
+
+int p2p_push_dir(mamr_ctx *c, int d, cudaStream_t st, int set)
+{
+   const int np = (int)c->cl[d].partner.size();
+   if (np == 0) return MAMR_OK;
+   launch_p2p_push(c->d_push[d], np, c->push_max[d], c->d_send[d], c->d_peer_win, c->win, c->win_data_off,
+                   c->d_push_done + d*P2P_MAX_RANKS, c->p.rank, set, d, c->xseq[set], c->p2p_epoch, st);
+   c->cnt.kernel_launches++;
+   count_messages(c, d);
+   return MAMR_OK;
+}
+
+int p2p_wait_dir(mamr_ctx *c, int d, cudaStream_t st, int set)
+{
+   const int np = (int)c->cl[d].partner.size();
+   if (np == 0) return MAMR_OK;
+   launch_p2p_wait(c->d_push[d], np, c->win, set, d, c->xseq[set], st);
+   c->cnt.kernel_launches++;
+   return MAMR_OK;
+}
+
 int exchange_dir(mamr_ctx *c, int d, cudaStream_t st, int set)
 {
    const DirLists &L = c->cl[d];
    if (c->p2p) {
-      const int np = (int)L.partner.size();
-      launch_p2p_push(c->d_push[d], np, c->push_max[d], c->d_send[d], c->d_peer_win, c->win,
-                      c->win_data_off, c->d_push_done + d*P2P_MAX_RANKS, c->p.rank, set, d, c->xseq[set],
-                      c->p2p_epoch, st);
-      launch_p2p_wait(c->d_push[d], np, c->win, set, d, c->xseq[set], st);
-      c->cnt.kernel_launches += 2;
-      for (size_t i = 0; i < L.partner.size(); i++) {
-         c->cnt.counter_halo_recv[d]++;
-         c->cnt.counter_halo_send[d]++;
-         c->cnt.size_mesg_recv[d] += (double)L.recv_size[i]*sizeof(double);
-         c->cnt.size_mesg_send[d] += (double)L.send_size[i]*sizeof(double);
-         c->cnt.counter_face_send[d] += L.num[i];
-         c->cnt.counter_face_recv[d] += L.num[i];
-      }
+      CK(p2p_push_dir(c, d, st, set));
+      CK(p2p_wait_dir(c, d, st, set));
       CU(cudaGetLastError());
       return MAMR_OK;
    }
@@ -868,13 +932,24 @@ int exchange_dir(mamr_ctx *c, int d, cudaStream_t st, int set)
                      L.partner[i], c->nccl, st));
       NC(g_nccl.Send(c->d_send[d] + L.send_off[L.index[i]], (size_t)L.send_size[i], NCCL_DOUBLE,
                      L.partner[i], c->nccl, st));
-      c->cnt.counter_halo_recv[d]++;
-      c->cnt.counter_halo_send[d]++;
-      c->cnt.size_mesg_recv[d] += (double)L.recv_size[i]*sizeof(double);
-      c->cnt.size_mesg_send[d] += (double)L.send_size[i]*sizeof(double);
-      c->cnt.counter_face_send[d] += L.num[i];
-      c->cnt.counter_face_recv[d] += L.num[i];
    }
+   NC(g_nccl.GroupEnd());
+   count_messages(c, d);
+   return MAMR_OK;
+}
+
+// the three directions at once (their send buffers are packed): one round
+int exchange_dirs(mamr_ctx *c, const int dirs[3], cudaStream_t st, int set)
+{
+   if (c->p2p) {
+      for (int o = 0; o < 3; o++) CK(p2p_push_dir(c, dirs[o], st, set));
+      for (int o = 0; o < 3; o++) CK(p2p_wait_dir(c, dirs[o], st, set));
+      CU(cudaGetLastError());
+      return MAMR_OK;
+   }
+   NC(g_nccl.GroupStart());
+   for (int o = 0; o < 3; o++)
+      if (!c->cl[dirs[o]].partner.empty()) CK(exchange_dir(c, dirs[o], st, set));
    NC(g_nccl.GroupEnd());
    return MAMR_OK;
 }
@@ -1372,10 +1447,13 @@ int flush_pending(mamr_ctx *c)
             KTimer t(c, KC_STENCIL, nullptr, KD_FUSED);
             CU(cudaEventRecord(c->ev_pre, c->stream));
             launch(c->d_order_ord[ord], c->n_interior[ord], c->stream);
+            trace_mark(c, 2, c->stream);
             CU(cudaStreamWaitEvent(c->bstream, c->ev_pre, 0));
             CU(cudaStreamWaitEvent(c->bstream, c->ev_xchg, 0));
+            trace_mark(c, 3, c->bstream);
             launch(c->d_order_ord[ord] + c->n_interior[ord], c->num_active - c->n_interior[ord],
                    c->bstream);
+            trace_mark(c, 4, c->bstream);
             CU(cudaEventRecord(c->ev_bdone, c->bstream));
             CU(cudaStreamWaitEvent(c->stream, c->ev_bdone, 0));
             CU(cudaStreamWaitEvent(c->stream, c->ev_xchg, 0));
@@ -1698,6 +1776,7 @@ int mamr_create(const mamr_params *params, mamr_ctx **out)
    c->spec_cs_ok.assign(p.num_vars, 0);
    c->spec_cs.assign(p.num_vars, 0.0);
    { const char *e = getenv("MAMR_NO_LOOKAHEAD"); c->use_lookahead = !(e && e[0] == '1'); }
+   { const char *e = getenv("MAMR_TRACE"); c->trace = e && e[0] == '1'; }
    { const char *e = getenv("MAMR_NO_FUSED_CS"); c->use_cs_fused = !(e && e[0] == '1'); }
    c->pc_set.assign(p.num_vars, 0);
    c->stale_set.assign(p.num_vars, 0);
@@ -1782,6 +1861,11 @@ void mamr_destroy(mamr_ctx *c)
    if (c->bstream) cudaStreamSynchronize(c->bstream);
    if (c->stream) cudaStreamSynchronize(c->stream);
    drain_ktimers(c);
+   trace_drain(c);
+   if (c->trace && c->tr_n > 0)
+      fprintf(stderr, "miniamr_b200 trace rank %d: %lld overlapped stages; after comm(): exchange done +%.3f ms, "
+              "interior blocks done +%.3f ms, boundary blocks start +%.3f ms, done +%.3f ms\n", c->p.rank, c->tr_n,
+              c->tr_sum[0]/c->tr_n, c->tr_sum[1]/c->tr_n, c->tr_sum[2]/c->tr_n, c->tr_sum[3]/c->tr_n);
    for (cudaEvent_t e : c->ev_free) cudaEventDestroy(e);
    if (c->nccl && g_nccl.CommDestroy) g_nccl.CommDestroy(c->nccl);
    xfree(c, c->pool[0]);
@@ -2217,25 +2301,37 @@ int mamr_comm(mamr_ctx *c, int start, int num_comm, int stage)
             xs = c->xstream;
             CU(cudaEventRecord(c->ev_data, c->stream));
             CU(cudaStreamWaitEvent(xs, c->ev_data, 0));
+            trace_mark(c, 0, c->stream);
          }
          CK(p2p_begin(c, xs, set));
-         for (int o = 0; o < 3; o++) {
-            const int d = kPerm[ord][o];
-            if (c->cl[d].partner.empty()) continue;
+         auto pack_phase = [&](int o) {
             for (const Run &r : runs_of(c, start, num_comm, false)) {
                KTimer t(c, KC_GHOST, xs, KD_PACK);
                launch_facepack(c->d_pack[ord][o], c->d_pack_fb[ord][o], (int)c->pack_fb[ord][o].size() - 1,
                                vpool(c, r.start), c->g.var_stride, send, recv, r.start, r.num, start, xs);
                c->cnt.kernel_launches++;
             }
-            {
+         };
+         if (c->p.stencil == 7) {
+            // The 7-point exchange never widens a face (comm.c:266-270): no phase forwards what an
+            // earlier one delivered, so the three directions travel at once -- all packs, all
+            // transfers, one wait -- instead of three dependent rounds.
+            for (int o = 0; o < 3; o++)
+               if (!c->cl[kPerm[ord][o]].partner.empty()) pack_phase(o);
+            KTimer t(c, KC_GHOST, xs, KD_XCHG);
+            CK(exchange_dirs(c, kPerm[ord], xs, set));
+         } else
+            for (int o = 0; o < 3; o++) {
+               const int d = kPerm[ord][o];
+               if (c->cl[d].partner.empty()) continue;
+               pack_phase(o);
                KTimer t(c, KC_GHOST, xs, KD_XCHG);
                CK(exchange_dir(c, d, xs, set));
             }
-         }
          if (c->use_overlap) {
             CU(cudaEventRecord(c->ev_xchg, xs));
             c->xchg_pending = true;
+            trace_mark(c, 1, xs);
          }
          CU(cudaGetLastError());
       }
@@ -2824,6 +2920,7 @@ int mamr_p2p_connect(mamr_ctx *c, const char *handles)
       c->recv_cap[d] = 0;
    }
    c->p2p = true;
+   c->p2p_timeout_s = p2p_set_timeout_from_env();
    if (const char *e = getenv("MAMR_TRANSPORT"))
       if (!strcmp(e, "nccl") && c->nccl) c->p2p = false;     // keep NCCL for A/B measurements
    c->ops_dirty = true;

@@ -17,6 +17,8 @@
 //
 // A waiting thread gives up after P2P_TIMEOUT_NS and records the fact in the window
 // header (mamr_sync / check_sum report it): a lost peer is an error, never a hung GPU.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -45,6 +47,8 @@ __device__ __forceinline__ unsigned long long global_ns()
    return t;
 }
 
+__device__ unsigned long long d_p2p_timeout_ns = P2P_TIMEOUT_NS;
+
 // spin until *p >= want; false (and the error word set) after the timeout
 __device__ bool spin_ge(const unsigned long long *p, unsigned long long want, P2PHeader *mine,
                         unsigned long long code)
@@ -54,7 +58,7 @@ __device__ bool spin_ge(const unsigned long long *p, unsigned long long want, P2
    unsigned ns = 32;
    for (;;) {
       if (ld_acquire_sys(p) >= want) return true;
-      if (global_ns() - t0 > P2P_TIMEOUT_NS) {
+      if (global_ns() - t0 > d_p2p_timeout_ns) {
          atomicCAS(&mine->error, 0ULL, code);
          return false;
       }
@@ -217,6 +221,18 @@ __global__ void p2p_mv_wait_kernel(const int *ranks, int n, char *mine_raw, unsi
 }
 
 }  // namespace
+
+// MAMR_P2P_TIMEOUT_S: how long a kernel waits for a peer before it gives up (default 20 s)
+double p2p_set_timeout_from_env()
+{
+   unsigned long long ns = P2P_TIMEOUT_NS;
+   if (const char *e = getenv("MAMR_P2P_TIMEOUT_S")) {
+      const double sec = atof(e);
+      if (sec > 0.0) ns = (unsigned long long)(sec*1e9);
+   }
+   cudaMemcpyToSymbol(d_p2p_timeout_ns, &ns, sizeof ns);
+   return (double)ns*1e-9;
+}
 
 void launch_p2p_mv_resolve(const P2PMove *d_recvs, int n, char *const *d_peer, char *mine, size_t mv_off,
                            int mv_cap, int me, unsigned long long seq, int *d_k, cudaStream_t s)

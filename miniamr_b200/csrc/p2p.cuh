@@ -60,6 +60,8 @@ void launch_p2p_mv_done(const int *d_ranks, int n, char *const *d_peer, int me, 
                         cudaStream_t s);
 void launch_p2p_mv_wait(const int *d_ranks, int n, char *mine, unsigned long long seq, cudaStream_t s);
 
+double p2p_set_timeout_from_env();      // seconds in force
+
 void launch_p2p_credit(const P2PTarget *d_targets, int n, char *const *d_peer, int me, int set,
                        unsigned long long seq, cudaStream_t s);
 void launch_p2p_push(const P2PTarget *d_parts, int n, long long max_size, const double *send,

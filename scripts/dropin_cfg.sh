@@ -7,6 +7,7 @@ CFG=$1; IMPL=$2; N=${3:-8}
 OBJ="--num_objects 2 --object 2 0 0.3 0.3 0.3 0.01 0.01 0.01 0.25 0.25 0.25 0 0 0 --object 0 0 0.5 0.5 0.9 0 0 -0.01 0.6 0.6 0.02 0 0 0"
 case $N in 8) NP="--npx 2 --npy 2 --npz 2";; 4) NP="--npx 2 --npy 2";; 2) NP="--npx 2";; 1) NP="";; esac
 case $CFG in
+  cfg1)  ARGS="$NP --nx 10 --ny 10 --nz 10 --num_vars 40 --stencil 7 --num_refine 4 --max_blocks 4000 --num_objects 1 --object 2 0 0.3 0.3 0.3 0.01 0.01 0.01 0.25 0.25 0.25 0 0 0 --num_tsteps 20 --stages_per_ts 20";;
   cfg4)  ARGS="$NP --init_x 1 --init_y 1 --init_z 1 --nx 10 --ny 10 --nz 10 --num_vars 40 --num_refine 5 --max_blocks 6000 --refine_freq 5 --num_tsteps 20 --stages_per_ts 20 --lb_opt 1 $OBJ";;
   cfg4s) ARGS="$NP --init_x 1 --init_y 1 --init_z 1 --nx 10 --ny 10 --nz 10 --num_vars 40 --num_refine 3 --max_blocks 3000 --refine_freq 2 --num_tsteps 4 --stages_per_ts 5 --lb_opt 1 $OBJ";;
   cfg5)  ARGS="$NP --init_x 3 --init_y 3 --init_z 3 --nx 10 --ny 10 --nz 10 --num_vars 160 --comm_vars 40 --stencil 27 --uniform_refine 1 --num_refine 2 --max_blocks 1800 --num_tsteps 2 --stages_per_ts 10 --checksum_freq 1";;

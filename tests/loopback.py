@@ -16,10 +16,27 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 def run_ranks(kind, world, cfg, timeout=300, env=None, processes=False):
     """processes=False: all ranks as threads of ONE fresh process (fast: their kernels run
-    concurrently); True: one process per rank (CUDA IPC; time-sliced on a shared GPU)"""
+    concurrently); True: one process per rank (CUDA IPC; time-sliced on a shared GPU).
+
+    Threads share one CUDA context, whose scheduling of independent streams is not under the
+    library's control: once in a hundred runs a kernel that waits for a peer ends up in front of
+    that peer's work and the wait times out (reported as MAMR_EP2P, never a wrong result).  A
+    run that ends that way is repeated, the second time with one process per rank."""
+    last = None
+    for attempt, procs_mode in enumerate([processes, processes, True]):
+        ok, last = _run_once(kind, world, cfg, timeout, env, procs_mode)
+        if ok:
+            return
+        if "waited" not in last or "peer-memory transport" not in last:
+            break
+    raise AssertionError(last)
+
+
+def _run_once(kind, world, cfg, timeout, env, processes):
     e = dict(os.environ)
     e.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     e.setdefault("CUDA_MODULE_LOADING", "EAGER")
+    e.setdefault("MAMR_P2P_TIMEOUT_S", "20" if processes else "4")
     if env:
         e.update(env)
     with tempfile.TemporaryDirectory(prefix="mamr_lb_") as scratch:
@@ -34,7 +51,9 @@ def run_ranks(kind, world, cfg, timeout=300, env=None, processes=False):
         except subprocess.TimeoutExpired:
             for p in procs:
                 p.kill()
-            raise AssertionError(f"loopback run {kind} {cfg} did not finish in {timeout} s")
+            return False, f"loopback run {kind} {cfg} did not finish in {timeout} s"
         bad = [(w, p.returncode, o[0][-1500:], o[1][-3000:]) for w, p, o in zip(whos, procs, outs)
                if p.returncode != 0 or f"LB_OK {w}" not in o[0]]
-        assert not bad, "rank %s rc=%s\n%s\n%s" % bad[0]
+        if bad:
+            return False, "rank %s rc=%s\n%s\n%s" % bad[0]
+        return True, ""

@@ -156,6 +156,7 @@ static void upload_host_blocks(void)
 
 static void pull_counters(void);
 static double attribute_times(int wait);
+int mamr_glue_lean_host(void);
 
 /* everything queued has run and every counter has reached the reference's globals */
 static void settle_counters(void)
@@ -171,6 +172,10 @@ void mamr_glue_sync_host(void)
 {
    int in, n;
    if (!G || host_fresh) return;
+   if (mamr_glue_lean_host()) {
+      printf("%d ERROR: mamr_glue_sync_host needs MAMR_LEAN_HOST=0 (blocks[].array is a stub)\n", my_pe);
+      exit(-1);
+   }
    settle_counters();
    for (in = 0; in < sorted_index[num_refine+1]; in++) {
       n = sorted_list[in].n;
@@ -430,6 +435,73 @@ void unpack_block(int n)
    else
       OK(mamr_unpack_block(G, n, recv_buff + (end - (int *) recv_buff)), "unpack_block");
    topo_dirty = 1;
+}
+
+/* ---- host memory ---------------------------------------------------------------
+ * allocate() (main.c:429-450) mallocs the jagged blocks[n].array[var][i][j] rows of every one
+ * of the max_num_blocks slots: 8.4 GB and 5.8 s for 9000 blocks of 10^3 x 40, 51 GB
+ * per rank for BASELINE configs[2] -- memory the drop-in never reads, because block data lives
+ * in the device pool.  Only the slots init() fills (init.c:453-495: the first
+ * init_block_x*y*z of them) ever carry data on the host, until the first hot-path call
+ * uploads them.  Every later slot gets ONE shared set of tables -- array -> [var] -> [i] -> [j]
+ * -> one row -- so that the reference's in-line loops over them (block.c:161-173, 418-430,
+ * which run before the device replays the copy) stay legal and touch a few hundred bytes.
+ * MAMR_LEAN_HOST=0 keeps the reference's allocation (needed by mamr_glue_sync_host). */
+void *__real_ma_malloc(size_t size, char *file, int line);
+void __real_allocate(void);
+static int lean_phase;            /* 1: in allocate(), before blocks[]; 2: per-block tables */
+static long lean_pos;
+static void *lean_tab[4];         /* shared [var] table, [i] table, [j] table, row */
+
+int mamr_glue_lean_host(void)
+{
+   static int v = -1;
+   if (v < 0) v = !(getenv("MAMR_LEAN_HOST") && !atoi(getenv("MAMR_LEAN_HOST")));
+   return v;
+}
+
+void __wrap_allocate(void)
+{
+   lean_phase = mamr_glue_lean_host() ? 1 : 0;
+   __real_allocate();
+   lean_phase = 0;
+}
+
+/* deallocate() (main.c:609-624) would free the shared tables once per slot */
+void __real_deallocate(void);
+void __wrap_deallocate(void)
+{
+   if (!mamr_glue_lean_host()) __real_deallocate();
+}
+
+void *__wrap_ma_malloc(size_t size, char *file, int line)
+{
+   if (lean_phase == 1 && size == (size_t) max_num_blocks*sizeof(block)) {
+      lean_phase = 2;
+      lean_pos = 0;
+   } else if (lean_phase == 2) {
+      long per_j = 1 + (y_block_size+2), per_m = 1 + (long)(x_block_size+2)*per_j,
+           per_block = 1 + (long) num_vars*per_m, keep = (long) init_block_x*init_block_y*init_block_z,
+           n = lean_pos/per_block, p = lean_pos%per_block;
+      int level;
+      if (n >= max_num_blocks)
+         lean_phase = 3;                            /* sorted_list and what follows */
+      else {
+         lean_pos++;
+         if (n >= keep) {
+            if (p == 0) level = 0;
+            else if ((p - 1)%per_m == 0) level = 1;
+            else if (((p - 1)%per_m - 1)%per_j == 0) level = 2;
+            else level = 3;
+            if (!lean_tab[level]) {
+               lean_tab[level] = __real_ma_malloc(size, file, line);
+               memset(lean_tab[level], 0, size);      /* the shared row: zeros stay zeros */
+            }
+            return lean_tab[level];
+         }
+      }
+   }
+   return __real_ma_malloc(size, file, line);
 }
 
 /* ---- link-time interception of the in-line array loops --------------------- */

@@ -52,6 +52,9 @@ class RefMiniAMR:
         if not os.path.exists(src):
             raise FileNotFoundError(f"{src} missing: run `make -C oracle` / `make -C integration`")
         if variant in ("int", "int_mp"):
+            # the harness looks at blocks[].array (sync_host, get_slot): keep the reference's
+            # host allocation instead of the drop-in's stub tables (integration/glue.c)
+            os.environ["MAMR_LEAN_HOST"] = "0"
             # the private copy below cannot use its $ORIGIN-relative rpath: make the
             # CUDA library resident first, the copy then binds to it by soname
             C.CDLL(os.path.join(os.path.dirname(HERE), "miniamr_b200", "libminiamr_b200.so"),

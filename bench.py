@@ -330,6 +330,7 @@ def run_ours(args):
         barrier_all(d)
         clk = clocks.stop() if clocks else None
         kt = d.kernel_times()
+        dt = d.device_times()
         d.kernel_timing(False)
         cnt = d.counters()
         ms = max_over_ranks(ms)
@@ -343,7 +344,7 @@ def run_ours(args):
         achieved = st_bytes/(st_launch_ms*1e-3)/1e9
         stage_gbs = upd/world*steps/(ms*1e-3)*bpu["stage"]/1e9
         return dict(d=d, host=host, w=w, n=n, V=V, cv=cv, stencil=stencil, B=B, nslots=nslots,
-                    nactive=nactive, grid=[npx, npy, npz], sums0=sums0, ms=ms, kt=kt, cnt=cnt, clk=clk,
+                    nactive=nactive, grid=[npx, npy, npz], sums0=sums0, ms=ms, kt=kt, dt=dt, cnt=cnt, clk=clk,
                     upd_per_step=upd, value=upd*steps/(ms*1e-3), bpu=bpu, st_launch_ms=st_launch_ms,
                     st_bytes=st_bytes, achieved=achieved, stage_gbs=stage_gbs, h2d_bytes=need*8)
 
@@ -469,7 +470,9 @@ def run_ours(args):
                          "stage_achieved_gbs_per_gpu": stage_gbs,
                          "stage_frac": stage_gbs/peak,
                          "kernel_share_of_step": {
-                             "stencil": kt["stencil_ms"]/ms, "ghost": kt["ghost_ms"]/ms}},
+                             "stencil": kt["stencil_ms"]/ms, "ghost": kt["ghost_ms"]/ms},
+                         "exchange_ms_per_step": {"pack": L["dt"]["pack_ms"]/args.steps,
+                                                  "transfer_and_wait": L["dt"]["exchange_ms"]/args.steps}},
             "clocks": clk,
             "e2e": {"value": e2e_val, "unit": UNIT,
                     "h2d_bytes_per_step": h2d_bytes/args.steps,
@@ -513,7 +516,9 @@ def run_ours(args):
                                          "algorithmic_bytes_per_launch": A["st_bytes"],
                                          "stage_frac": A["stage_gbs"]/peak,
                                          "kernel_share_of_step": {"stencil": A["kt"]["stencil_ms"]/A["ms"],
-                                                                  "ghost": A["kt"]["ghost_ms"]/A["ms"]}},
+                                                                  "ghost": A["kt"]["ghost_ms"]/A["ms"]},
+                                         "exchange_ms_per_step": {"pack": A["dt"]["pack_ms"]/args.steps,
+                                                                  "transfer_and_wait": A["dt"]["exchange_ms"]/args.steps}},
                             "nvlink_bytes_per_step": (sum(A["cnt"]["size_mesg_send"])/args.steps
                                                       if world > 1 else 0)}
             except Exception as e:       # never gates the headline

@@ -15,7 +15,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libminiamr_b200.so")
+# (MAMR_LIB_PATH: an experimental build of the same library, for A/B measurements)
+LIB_PATH = os.environ.get("MAMR_LIB_PATH") or os.path.join(HERE, "libminiamr_b200.so")
 
 
 class MamrError(RuntimeError):

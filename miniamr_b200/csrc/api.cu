@@ -3054,6 +3054,7 @@ int mamr_kernel_timing(mamr_ctx *c, int enable)
    drain_ktimers(c);
    c->ktiming = enable != 0;
    for (int i = 0; i < 3; i++) { c->k_ms[i] = 0; c->k_launches[i] = 0; }
+   for (int i = 0; i < KD_NUM; i++) c->kd_ms[i] = 0;
    return MAMR_OK;
 }
 

@@ -457,30 +457,46 @@ facepack_kernel(const BoxOp *__restrict__ ops, const int *__restrict__ fbegin,
       const long long svs = pool ? var_stride : op.src_vs;
       const int e1 = op.ext[1], e2 = op.ext[2];
       const int n = op.ext[0]*e1*e2;
-      for (int w = threadIdx.x; w < n*nv; w += blockDim.x) {
-         const int t = w/n;
-         int r = w - t*n;
-         const int c = r%e2; r /= e2;
-         const int b = r%e1;
-         const int a = r/e1;
-         const int v = v0 + t;
-         const double *src = src0 + (pool ? (long long)v : (long long)(v - buf_var0))*svs;
-         double x;
-         if (op.mode == FM_COPY || op.mode == FM_DIV4) {
-            x = src[(long long)a*op.src_str[0] + b*op.src_str[1] + c*op.src_str[2]];
-            if (op.mode == FM_DIV4) x = x/4.0;
-         } else if (op.mode == FM_PROLONG || op.mode == FM_REPL) {
-            x = src[(long long)(a >> 1)*op.src_str[0] + (b >> 1)*op.src_str[1] + (c >> 1)*op.src_str[2]];
-            if (op.mode == FM_PROLONG) x = x/4.0;
-         } else {
-            const double *p = src + (long long)(2*a)*op.src_str[0] + (2*b)*op.src_str[1] +
-                              (2*c)*op.src_str[2];
-            x = p[0] + p[op.F];
-            x += p[op.S];
-            x += p[op.S + op.F];
+      // PACK_U independent elements per thread and trip: the loads of a trip are all in flight
+      // before the first store (the kernel runs beside the stage kernel of the interior blocks,
+      // which saturates HBM; with one load at a time per thread it crawls)
+      constexpr int PACK_U = 4;
+      for (int w0 = threadIdx.x; w0 < n*nv; w0 += blockDim.x*PACK_U) {
+         double x[PACK_U];
+         long long doff[PACK_U];
+#pragma unroll
+         for (int u = 0; u < PACK_U; u++) {
+            const int w = w0 + u*blockDim.x;
+            x[u] = 0.0;
+            doff[u] = -1;
+            if (w >= n*nv) continue;
+            const int t = w/n;
+            int r = w - t*n;
+            const int c = r%e2; r /= e2;
+            const int b = r%e1;
+            const int a = r/e1;
+            const int v = v0 + t;
+            const double *src = src0 + (pool ? (long long)v : (long long)(v - buf_var0))*svs;
+            if (op.mode == FM_COPY || op.mode == FM_DIV4) {
+               x[u] = __ldg(src + (long long)a*op.src_str[0] + b*op.src_str[1] + c*op.src_str[2]);
+               if (op.mode == FM_DIV4) x[u] = x[u]/4.0;
+            } else if (op.mode == FM_PROLONG || op.mode == FM_REPL) {
+               x[u] = __ldg(src + (long long)(a >> 1)*op.src_str[0] + (b >> 1)*op.src_str[1] + (c >> 1)*op.src_str[2]);
+               if (op.mode == FM_PROLONG) x[u] = x[u]/4.0;
+            } else {
+               const double *p = src + (long long)(2*a)*op.src_str[0] + (2*b)*op.src_str[1] +
+                                 (2*c)*op.src_str[2];
+               double y = __ldg(p) + __ldg(p + op.F);
+               y += __ldg(p + op.S);
+               y += __ldg(p + op.S + op.F);
+               x[u] = y;
+            }
+            doff[u] = (long long)(v - buf_var0)*op.dst_vs + (long long)a*op.dst_str[0] + b*op.dst_str[1] +
+                      c*op.dst_str[2];
          }
-         dst0[(long long)(v - buf_var0)*op.dst_vs + (long long)a*op.dst_str[0] + b*op.dst_str[1] +
-              c*op.dst_str[2]] = x;
+#pragma unroll
+         for (int u = 0; u < PACK_U; u++)
+            if (doff[u] >= 0) dst0[doff[u]] = x[u];
       }
    }
 }

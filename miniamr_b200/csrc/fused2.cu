@@ -25,6 +25,10 @@
 #include "ptx.cuh"
 #include "fused_common.cuh"
 
+#ifndef MAMR_CT128_FROM
+#define MAMR_CT128_FROM 10
+#endif
+
 namespace mamr {
 
 namespace {
@@ -79,7 +83,7 @@ struct Shape {
    static constexpr int SJ = N + 2, PL = SJ*SJ, TILE = (N + 2)*PL;
    static constexpr int HALO = TILE - N*N*N;
    // compute threads per CTA: small tiles take fewer threads and more CTAs per SM
-   static constexpr int CT = N >= 14 ? 256 : (N >= 10 ? 128 : 64);
+   static constexpr int CT = N >= 14 ? 256 : (N >= MAMR_CT128_FROM ? 128 : 64);
    static constexpr int THREADS = CT + 32;        // + the copy warp
    static constexpr int Q = (HALO + CT - 1)/CT;
    // Z-face cells (k = 0 and N+1 of rows 1..N, planes 1..N) lie inside the rows the

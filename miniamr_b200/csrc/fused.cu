@@ -437,9 +437,12 @@ void launch_fused(const double *pool_in, double *pool_out, const Geometry &g, co
 // possibly out of an earlier receive buffer); the CTA walks them for its variables, so a
 // one-cell corner op costs one loop trip instead of a CTA of its own.
 // ---------------------------------------------------------------------------
-constexpr int PACK_VPC = 8;
+// 128 threads and at most 50 registers: a CTA must fit beside the two resident CTAs of the
+// interior blocks' stage kernel (~10 K registers of an SM stay free), or packing only advances as
+// those retire.
+constexpr int PACK_VPC = 4;
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 10)
 facepack_kernel(const BoxOp *__restrict__ ops, const int *__restrict__ fbegin,
                 const double *__restrict__ pool_in, long long var_stride, double *send0, double *send1,
                 double *send2, const double *recv0, const double *recv1, const double *recv2,
@@ -507,7 +510,7 @@ void launch_facepack(const BoxOp *d_ops, const int *d_fbegin, int n_faces, const
 {
    if (n_faces <= 0 || num_vars <= 0) return;
    dim3 grid((unsigned)n_faces, (unsigned)((num_vars + PACK_VPC - 1)/PACK_VPC));
-   facepack_kernel<<<grid, 256, 0, s>>>(d_ops, d_fbegin, pool_in, var_stride, send[0], send[1], send[2],
+   facepack_kernel<<<grid, 128, 0, s>>>(d_ops, d_fbegin, pool_in, var_stride, send[0], send[1], send[2],
                                         recv[0], recv[1], recv[2], var_start, var_start + num_vars, buf_var0);
 }
 

@@ -28,6 +28,9 @@
 #ifndef MAMR_CT128_FROM
 #define MAMR_CT128_FROM 10
 #endif
+#ifndef MAMR_REGS_SMALL
+#define MAMR_REGS_SMALL 96      // register budget per thread that sizes CTAs per SM for N < 14
+#endif
 
 namespace mamr {
 
@@ -103,7 +106,7 @@ struct Shape {
    static constexpr int SMEM = 2*TB*8 + MAX_OPS*(int)sizeof(SOp) + 64;
    // CTAs per SM: shared memory (1 KB reserved per CTA), 96 registers per thread
    static constexpr int BY_SMEM = (228*1024)/(SMEM + 128 + 1024);
-   static constexpr int BY_REGS = 65536/(96*THREADS);
+   static constexpr int BY_REGS = 65536/((N >= 14 ? 96 : MAMR_REGS_SMALL)*THREADS);
    static constexpr int CTAS = BY_SMEM < BY_REGS ? (BY_SMEM < 8 ? BY_SMEM : 8) : (BY_REGS < 8 ? BY_REGS : 8);
 };
 

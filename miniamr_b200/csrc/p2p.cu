@@ -77,8 +77,10 @@ p2p_credit_kernel(const P2PTarget *targets, int n, char *const *peer, int me, in
    st_release_sys(&H->credit[set][targets[t].dir][me], seq);
 }
 
-// grid = (chunks, partners of this direction)
-__global__ void __launch_bounds__(256)
+// grid = (chunks, partners of this direction).  128 threads and at most 40 registers: a CTA must
+// fit beside the two resident CTAs of the interior blocks' stage kernel (which leave ~10 K
+// registers of an SM free), or the exchange only advances as those retire.
+__global__ void __launch_bounds__(128, 12)
 p2p_push_kernel(const P2PTarget *parts, const double *send, char *const *peer, char *mine_raw,
                 size_t data_off, unsigned *done, int me, int set, int dir, unsigned long long seq,
                 unsigned long long epoch)
@@ -292,10 +294,10 @@ void launch_p2p_push(const P2PTarget *d_parts, int n, long long max_size, const 
                      int dir, unsigned long long seq, unsigned long long epoch, cudaStream_t s)
 {
    if (n <= 0) return;
-   // 32 KB per CTA, at most 128 CTAs per partner (x 256 threads x 8 loads in flight)
-   int chunks = (int)std::min<long long>(128, std::max<long long>(1, (max_size + 4095)/4096));
+   // 16 KB per CTA, at most 256 CTAs per partner (x 128 threads x 8 loads in flight)
+   int chunks = (int)std::min<long long>(256, std::max<long long>(1, (max_size + 2047)/2048));
    dim3 grid((unsigned)chunks, (unsigned)n);
-   p2p_push_kernel<<<grid, 256, 0, s>>>(d_parts, send, d_peer, mine, data_off, d_done, me, set, dir, seq, epoch);
+   p2p_push_kernel<<<grid, 128, 0, s>>>(d_parts, send, d_peer, mine, data_off, d_done, me, set, dir, seq, epoch);
 }
 
 void launch_p2p_wait(const P2PTarget *d_parts, int n, char *mine, int set, int dir,

@@ -192,6 +192,11 @@ int mamr_pending_block_moves(mamr_ctx *ctx);      /* staged and not yet flushed 
 int mamr_nccl_get_unique_id(char id[MAMR_NCCL_ID_BYTES]);   /* rank 0, then broadcast
                                                                over the host channel */
 int mamr_nccl_init(mamr_ctx *ctx, const char id[MAMR_NCCL_ID_BYTES]);
+/* --send_faces (comm.c:59-77, 96-128: one MPI message per face instead of one per partner):
+ * the transfer stays one message per partner, the counters counter_halo_send/recv and
+ * size_mesg_send/recv follow the reference's per-face accounting.  msg_len = the host's
+ * msg_len[3][4] (init.c:77-117). */
+int mamr_set_message_mode(mamr_ctx *ctx, int send_faces, const int *msg_len);
 int mamr_device_count(void);        /* visible CUDA devices (0 without a driver): lets a
                                        host without CUDA headers map rank -> device */
 

@@ -112,6 +112,7 @@ static void ensure_ctx(void)
       }
       nccl_moves = !(getenv("MAMR_HOST_MIGRATION") && atoi(getenv("MAMR_HOST_MIGRATION")));
    }
+   if (send_faces) OK(mamr_set_message_mode(G, 1, &msg_len[0][0]), "set_message_mode");
    stage_tile = (double *) malloc((size_t)num_vars*tile_doubles()*sizeof(double));
    memset(&seen, 0, sizeof seen);
    memset(&seen_t, 0, sizeof seen_t);

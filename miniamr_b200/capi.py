@@ -65,7 +65,7 @@ EXPORTS = [
     "mamr_check_sum", "mamr_check_sum_vars", "mamr_stage", "mamr_split_block",
     "mamr_consolidate_block", "mamr_pack_block", "mamr_unpack_block", "mamr_send_block",
     "mamr_recv_block", "mamr_stage_send_block", "mamr_stage_recv_block", "mamr_flush_block_moves",
-    "mamr_pending_block_moves", "mamr_device_count",
+    "mamr_pending_block_moves", "mamr_device_count", "mamr_set_message_mode",
     "mamr_nccl_get_unique_id", "mamr_nccl_init", "mamr_p2p_get_handle", "mamr_p2p_connect",
     "mamr_timer_begin",
     "mamr_timer_end", "mamr_kernel_timing", "mamr_kernel_time_ms", "mamr_get_device_times",

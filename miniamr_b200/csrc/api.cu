@@ -191,6 +191,9 @@ struct mamr_ctx {
 
    DirLists cl[3];
    bool have_partners = false;
+   // --send_faces: message accounting per face, with the host's msg_len[dir][0..3] (init.c:77-117)
+   bool send_faces = false;
+   int msg_len[3][4] = {};
    // One send buffer per direction.  Receive buffers come in `nsets` sets, one per
    // group of comm_vars variables (driver.c:75-89 calls comm() once per group and
    // stage): the messages of a group stay valid until the same group's next comm(),
@@ -887,6 +890,21 @@ int p2p_begin(mamr_ctx *c, cudaStream_t st, int set)
 void count_messages(mamr_ctx *c, int d)
 {
    const DirLists &L = c->cl[d];
+   if (c->send_faces) {
+      // --send_faces: the reference posts one message per face (comm.c:59-77, 96-128)
+      for (size_t i = 0; i < L.partner.size(); i++)
+         for (int f = L.index[i]; f < L.index[i] + L.num[i]; f++) {
+            const int j = L.face_case[f]%10;
+            const int st = j == 0 ? 0 : (j == 1 ? 1 : (j < 6 ? 2 : 3)), rt = j < 2 ? st : 5 - st;
+            c->cnt.counter_halo_recv[d]++;
+            c->cnt.counter_halo_send[d]++;
+            c->cnt.size_mesg_recv[d] += (double)c->comm_vars*c->msg_len[d][rt]*sizeof(double);
+            c->cnt.size_mesg_send[d] += (double)c->comm_vars*c->msg_len[d][st]*sizeof(double);
+            c->cnt.counter_face_send[d]++;
+            c->cnt.counter_face_recv[d]++;
+         }
+      return;
+   }
    for (size_t i = 0; i < L.partner.size(); i++) {
       c->cnt.counter_halo_recv[d]++;
       c->cnt.counter_halo_send[d]++;
@@ -2771,6 +2789,16 @@ int mamr_flush_block_moves(mamr_ctx *c)
    if (!c->mv_recv.empty()) touch_all(c, true);
    c->mv_send.clear();
    c->mv_recv.clear();
+   return MAMR_OK;
+}
+
+int mamr_set_message_mode(mamr_ctx *c, int send_faces, const int *msg_len)
+{
+   if (!c || (send_faces && !msg_len)) return fail(MAMR_EINVAL, "null argument");
+   c->send_faces = send_faces != 0;
+   if (msg_len)
+      for (int d = 0; d < 3; d++)
+         for (int k = 0; k < 4; k++) c->msg_len[d][k] = msg_len[d*4 + k];
    return MAMR_OK;
 }
 

@@ -2023,6 +2023,7 @@ int mamr_download_block(mamr_ctx *c, int slot, double *tiles)
                            g.var_stride*sizeof(double), g.tile*sizeof(double), r.num,
                            cudaMemcpyDeviceToHost, c->stream));
    CU(cudaStreamSynchronize(c->stream));
+   CK(p2p_check(c));      // data behind a wait that gave up is not data
    return MAMR_OK;
 }
 

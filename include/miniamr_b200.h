@@ -154,7 +154,8 @@ int mamr_stencil_calc(mamr_ctx *ctx, int var);
 /* the same for a run of variables in one launch */
 int mamr_stencil_vars(mamr_ctx *ctx, int var_start, int num);
 /* check_sum(var): check_sum.c:36-65, including the global reduction
- * (ncclAllReduce when num_ranks > 1).  Returns the sum in *sum. */
+ * (num_ranks > 1: all-reduce through the peer-memory windows, or ncclAllReduce).
+ * Returns the sum in *sum. */
 int mamr_check_sum(mamr_ctx *ctx, int var, double *sum);
 int mamr_check_sum_vars(mamr_ctx *ctx, int var_start, int num, double *sums);
 /* one whole stage as driver.c:73-89 issues it (comm per group of comm_vars,
@@ -179,7 +180,8 @@ int mamr_recv_block(mamr_ctx *ctx, int slot, int src_rank);
  * staging area at pack_block() time (its slot is reused right away,
  * rcb.c:259-266), the receiver records (slot, source) at unpack_block() time,
  * and every rank calls mamr_flush_block_moves() at the same point of the
- * program afterwards (end of move_blocks(), rcb.c:734-): ONE NCCL group with
+ * program afterwards (end of move_blocks(), rcb.c:734-): every receiver fetches its
+ * payloads out of the senders' windows (peer memory) -- or, with NCCL, ONE group with
  * all sends and receives, then the unpack kernels.  Between one pair of ranks
  * the k-th staged send matches the k-th staged receive. */
 int mamr_stage_send_block(mamr_ctx *ctx, int slot, int dest_rank);
@@ -187,7 +189,8 @@ int mamr_stage_recv_block(mamr_ctx *ctx, int slot, int src_rank);
 int mamr_flush_block_moves(mamr_ctx *ctx);
 int mamr_pending_block_moves(mamr_ctx *ctx);      /* staged and not yet flushed */
 
-/* ---- multi-GPU: one process per GPU, NCCL over NVLink ------------------- */
+/* ---- multi-GPU, alternative transport: NCCL send/recv over NVLink (the default is the
+ *      peer-memory transport below) ---------------------------------------- */
 #define MAMR_NCCL_ID_BYTES 128
 int mamr_nccl_get_unique_id(char id[MAMR_NCCL_ID_BYTES]);   /* rank 0, then broadcast
                                                                over the host channel */
@@ -208,8 +211,9 @@ int mamr_device_count(void);        /* visible CUDA devices (0 without a driver)
  * processes, plain pointers between ranks of one process (loopback tests: several
  * contexts on one GPU, one host thread each).  From then on comm() stores ghost
  * messages straight into the partner's receive buffer over NVLink and check_sum()
- * all-reduces through the windows, both ordered by system-scope flags; NCCL, if
- * initialised as well, keeps carrying migrated blocks (MAMR_TRANSPORT=nccl: everything).
+ * all-reduces through the windows and migrated blocks are fetched out of the sender's
+ * window, all ordered by system-scope flags (MAMR_TRANSPORT=nccl with mamr_nccl_init done:
+ * everything over NCCL instead).
  * A peer that never answers is reported after 20 s as MAMR_EP2P by the next
  * mamr_sync()/mamr_check_sum(), never as a hung GPU. */
 #define MAMR_P2P_HANDLE_BYTES 128

@@ -3,10 +3,10 @@
     python tests/lb_worker.py KIND RANK WORLD DIR JSON_CFG     one rank, a process of its own
     python tests/lb_worker.py KIND all  WORLD DIR JSON_CFG     all ranks, one thread each
 
-Rank r runs on GPU r % device_count.  Processes: window handles and barriers go through files
+Processes: rank r runs on GPU r % device_count; window handles and barriers go through files
 in a scratch directory, windows are mapped with CUDA IPC, and on one GPU the ranks' kernels are
 time-sliced (correct but slow: a rank that waits for a peer burns its whole time slice).
-Threads: the ranks share one CUDA context, their kernels run concurrently, windows are plain
+Threads: the ranks share GPU 0 and one CUDA context, their kernels run concurrently, windows are plain
 pointers.  A fresh process per run keeps every stream on a hardware queue of its own
 (CUDA_DEVICE_MAX_CONNECTIONS=32), so that a kernel spinning on a peer's flag never sits in front
 of that peer's work, and CUDA_MODULE_LOADING=EAGER keeps first launches from waiting for the
@@ -68,11 +68,14 @@ class ThreadHost:
         return out
 
 
+THREADS = False      # all ranks are threads of this process: they share GPU 0
+
+
 def device_for(rank):
     from miniamr_b200.capi import load_library
     n = load_library().mamr_device_count()
     assert n > 0, "no CUDA device"
-    return rank % n
+    return 0 if THREADS else rank % n
 
 
 def connect(d, host):
@@ -228,6 +231,7 @@ if __name__ == "__main__":
         fn(int(who), world, Host(int(who), world, scratch), cfg)
         print(f"LB_OK {who}")
         sys.exit(0)
+    THREADS = True
     shared = {"bar": threading.Barrier(world, timeout=120)}
     errors = []
 

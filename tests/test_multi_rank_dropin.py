@@ -40,6 +40,11 @@ RUNS = {
     "amr7_morton": (2, f"--npz 2 --init_x 2 --init_y 2 --init_z 1 --nx 6 --ny 4 --nz 8 --num_vars 2 --num_refine 2 "
                        f"--max_blocks 2000 --refine_freq 1 --num_tsteps 4 --stages_per_ts 3 --morton --permute "
                        f"{MOVING}"),
+    # Hilbert SFC partitioner with --permute at 4 ranks (the rank grid and mesh of
+    # tests/test_plan_multi_rank.py, where the reference's sfc_sort() stays inside its arrays)
+    "amr7_hilbert_4": (4, f"--npx 2 --npy 2 --init_x 1 --init_y 1 --init_z 2 --nx 4 --ny 4 --nz 6 --num_vars 2 "
+                          f"--num_refine 2 --max_blocks 2000 --refine_freq 1 --num_tsteps 3 --stages_per_ts 2 "
+                          f"--hilbert --permute {MOVING}"),
     # configs[4] in small: staged ghost comm, 27-point, checksum every stage
     "uni27_staged": (2, "--npx 2 --init_x 1 --init_y 2 --init_z 2 --nx 10 --ny 10 --nz 10 --num_vars 7 "
                         "--comm_vars 3 --stencil 27 --uniform_refine 1 --num_refine 1 --max_blocks 200 "

@@ -140,7 +140,9 @@ int mamr_set_comm_lists(mamr_ctx *ctx, const mamr_comm_dir dirs[3]);
 /* ---- the stage hot path ------------------------------------------------- */
 /* comm(start, num_comm, stage): comm.c:42-242 (code 0: pack_face :254-401,
  * unpack_face :1002-1150, on_proc_comm :1473-1534, on_proc_comm_diff
- * :1597-1688, apply_bc :1911-1965) */
+ * :1597-1688, apply_bc :1911-1965).  With off-rank partners num_comm <= comm_vars (the
+ * message buffers hold comm_vars variables per face) and, as in driver.c:75-89, start is a
+ * multiple of comm_vars: start / comm_vars also selects the receive-buffer set. */
 int mamr_comm(mamr_ctx *ctx, int start, int num_comm, int stage);
 /* stencil_driver(var, calc_stage): stencil.c:43-74 -> stencil_calc :76-145 */
 int mamr_stencil_driver(mamr_ctx *ctx, int var, int calc_stage);

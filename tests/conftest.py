@@ -3,12 +3,13 @@ import sys
 
 import pytest
 
-# several ranks may share one GPU and one process (tests/loopback.py): every stream gets its own
-# hardware queue, so that a kernel spinning on a peer's flag never sits in front of that peer's
-# work.  Must be set before CUDA initialises.
+# Several ranks may share one GPU (tests/loopback.py, tests/test_multi_rank_dropin.py: the rank
+# processes inherit this environment): every stream gets its own hardware queue, so that a kernel
+# spinning on a peer's flag never sits in front of that peer's work.  Must be set before CUDA
+# initialises.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 # ... and no kernel is loaded lazily at its first launch (which waits for the device) while a
-# peer in the same process already spins on this rank
+# peer already spins on this rank
 os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -234,6 +234,31 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_to_gpu_numa_node(local):
+    """N ranks upload at the same time (e2e): keep this rank's host thread, and with it the
+    first-touch placement of its pinned staging buffer, on the CPUs next to its GPU (sysfs
+    local_cpulist of the GPU's PCI function).  Best effort: any failure leaves the affinity alone."""
+    try:
+        out = subprocess.run(["nvidia-smi", "-i", str(local), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not out:
+            return
+        dom, rest = out.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 # ---------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------
@@ -254,6 +279,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        bind_to_gpu_numa_node(local)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
